@@ -1,0 +1,94 @@
+"""Scan driver and the ``calcBaller`` seam -- SURVEY.md §8 rows a5/a6.
+
+``calcBaller`` and ``Scan`` keep the reference's names, arguments and return values
+(/root/reference/BalLeRMix+_v1.py:436-507 and :510-640); the work is done by the
+CUDA library behind include/blmx.h.  ``Scan`` plans all centres of the run first
+(windows.py), sends them to the GPU in one ``blmx_scan`` call and then writes the
+rows with the reference's f-string formatting.
+"""
+from datetime import datetime
+
+import numpy as np
+
+from . import windows
+from .native import Scanner
+from .problem import build_problem
+
+HEADER = 'physPos\tgenPos\tCLR\tx_hat\ts_hat\tA_hat\tnSites\n'
+
+
+class DeviceScan:
+    """A problem resident on one GPU plus the grid objects needed to decode results."""
+
+    def __init__(self, InputData, NeutralSFS, NormalizedBetaBinom, Grids, device=0, group=None):
+        self.problem, self.order = build_problem(InputData, NeutralSFS, NormalizedBetaBinom, Grids)
+        self.scanner = Scanner(device=device, group=group).load(self.problem)
+
+    def run(self, t, lo, hi):
+        """-> (T float64[n], iA, ix, ia, nsites int32[n]); indices into the visiting order."""
+        return self.scanner.scan(t, lo, hi)
+
+    def decode(self, T, iA, ix, ia, ns):
+        return self.order.decode(T, iA, ix, ia, ns)
+
+    def close(self):
+        self.scanner.close()
+
+
+_cache = {}
+
+
+def calcBaller(window_indice, testSite, InputData, NeutralSFS, NormalizedBetaBinom, Grids):
+    """Drop-in for the reference function (v1:436): one centre, same 5-element result.
+
+    ``window_indice`` must be a contiguous ascending index range, which is all the
+    reference's callers ever pass (v1:538,572,589,606).
+    """
+    key = (id(InputData), id(NeutralSFS), id(NormalizedBetaBinom), id(Grids))
+    dev = _cache.get(key)
+    if dev is None:
+        _cache.clear()
+        dev = _cache[key] = DeviceScan(InputData, NeutralSFS, NormalizedBetaBinom, Grids)
+    w = np.asarray(window_indice)
+    if len(w) == 0:
+        return [0., 0., 0., 0., 0.]
+    if len(w) > 1 and not np.all(np.diff(w) == 1):
+        raise ValueError('window_indice must be a contiguous ascending range')
+    T, iA, ix, ia, ns = dev.run([float(testSite)], [int(w[0])], [int(w[-1])])
+    return dev.decode(T[0], iA[0], ix[0], ia[0], ns[0])
+
+
+def format_rows(plan, order, T, iA, ix, ia, ns):
+    """Output lines for a plan and its results (v1:535,540,574,591,607)."""
+    lines = []
+    for j in range(len(plan)):
+        if plan.gap[j]:
+            lines.append(plan.f0[j])
+            continue
+        Tm, xh, ah, Ah, w = order.decode(T[j], iA[j], ix[j], ia[j], ns[j])
+        lines.append(f'{plan.f0[j]}\t{plan.f1[j]}\t{Tm}\t{xh}\t{ah}\t{Ah}\t{w}\n')
+    return lines
+
+
+class Scan:
+    """Same constructor as the reference class (v1:613); runs the scan and writes ``outfile``."""
+
+    def __init__(self, InputData, NeutralSFS, NormalizedBetaBinom, Grids, outfile, fixSize=False,
+                 r=0, s=1, phys=False, noCenter=False, device=0):
+        plan = windows.make_plan(InputData, fixSize=fixSize, r=r, s=s, phys=phys, noCenter=noCenter)
+        print('writing output to %s' % (outfile))
+        dev = DeviceScan(InputData, NeutralSFS, NormalizedBetaBinom, Grids, device=device)
+        try:
+            t, lo, hi, gap = plan.arrays()
+            live = np.flatnonzero(~gap)
+            T = np.zeros(len(plan)); iA = np.full(len(plan), -1, np.int32)
+            ix = iA.copy(); ia = iA.copy(); ns = np.zeros(len(plan), np.int32)
+            if len(live):
+                T[live], iA[live], ix[live], ia[live], ns[live] = dev.run(t[live], lo[live], hi[live])
+            self.results = (T, iA, ix, ia, ns)
+            with open(outfile, 'w') as scores:
+                scores.write(HEADER)
+                scores.writelines(format_rows(plan, dev.order, T, iA, ix, ia, ns))
+        finally:
+            dev.close()
+        print(f'{datetime.now()}. Scan finished.')

@@ -1,0 +1,198 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI against
+the reference's goldens and against the CPU oracle.  Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = util.scan_cases()
+# two-class B1 tables make T of different (x, a) agree to ~1e-13 (see util.compare_scan)
+NEAR_TIES = {'Example2_B1': 12, 'Example1_B1': 8, 'ex1_B1_s80': 1, 'ex2_B1_listA_s10': 2}
+
+
+def run_cli(argv, out):
+    from ballermixplus_b200.cli import main
+    with util.quiet():
+        main(util.abs_paths(argv) + ['-o', out])
+    with open(out) as fh:
+        return fh.read().splitlines(keepends=True)
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_cli_scan_matches_reference_golden(name, tmp_path):
+    """Whole runs of the drop-in CLI (all rows) against the reference's output files."""
+    argv, gold = CASES[name]
+    lines = run_cli(argv, str(tmp_path / 'out.txt'))
+    n, same, worst, ties = util.compare_scan(lines, gold, rtol=1e-9, max_near_ties=NEAR_TIES.get(name, 0))
+    assert n == len(lines)
+    print(f'{name}: {n} rows, {same} byte-identical, max rel dCLR {worst:.2e}, near ties {ties}')
+
+
+def _problem(name):
+    from ballermixplus_b200.problem import build_problem
+    argv, _ = CASES[name]
+    opt, data, neutral, grid, sel = util.host_objects(argv)
+    prob, order = build_problem(data, neutral, sel, grid)
+    return data, prob, order
+
+
+def _check_against_oracle(prob, t, lo, hi, group=None, batch=None, rtol=1e-9):
+    from oracle import oracle_c
+    from ballermixplus_b200.native import Scanner
+    with Scanner(device=0, group=group, batch=batch).load(prob) as sc:
+        T, iA, ix, ia, ns = sc.scan(t, lo, hi)
+        pairs, _ = sc.counters()
+    rT, rA, rxa, rn, rpairs = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t, lo, hi)
+    bad = np.flatnonzero((iA != rA) | (ix * prob.n_a + ia != rxa) | (ns != rn))
+    bad = [j for j in bad if not (iA[j] < 0 and rA[j] < 0)]
+    assert np.all(np.abs(T - rT) <= rtol * np.maximum(np.abs(rT), 1.)), np.max(np.abs(T - rT))
+    assert pairs == rpairs
+    return T, iA, ix, ia, ns, bad
+
+
+@pytest.mark.parametrize('group', [1, 4])
+def test_ragged_windows_and_batches(group):
+    """Random, ragged, empty and out-of-range windows; small batches force several launches."""
+    data, prob, order = _problem('Example2_B2')
+    rng = np.random.default_rng(3)
+    n = 300
+    c = rng.integers(0, data.numSites, size=n)
+    t = data.genPos[c].copy()
+    t[::7] += 3e-7                                   # centres that are not sites
+    lo = c - rng.integers(0, 500, size=n)
+    hi = c + rng.integers(0, 500, size=n)
+    lo[::11] = hi[::11] + 5                          # empty windows
+    lo[::13] = -50                                   # clamped by the library
+    hi[::17] = data.numSites + 100
+    T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, group=group, batch=64)
+    assert not bad
+    empty = np.flatnonzero(lo > hi)
+    assert np.all(T[empty] == 0) and np.all(iA[empty] == -1) and np.all(ns[empty] == 0)
+
+
+def test_group1_and_group4_agree():
+    data, prob, order = _problem('Example1_B2maf')
+    from ballermixplus_b200.native import Scanner
+    c = np.arange(0, data.numSites, 5)
+    t, lo, hi = data.genPos[c], np.zeros(len(c), np.int64), np.full(len(c), data.numSites - 1, np.int64)
+    out = []
+    for g in (1, 4):
+        with Scanner(device=0, group=g).load(prob) as sc:
+            out.append(sc.scan(t, lo, hi))
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-12, atol=1e-12)
+    for a, b in zip(out[0][1:], out[1][1:]):
+        assert np.array_equal(a, b)
+
+
+def test_empty_inputs_and_errors():
+    from ballermixplus_b200.native import BlmxError, ScanProblem, Scanner
+    data, prob, order = _problem('ex1_B2_fixgrid')
+    with Scanner(device=0) as sc:
+        with pytest.raises(BlmxError):
+            sc.scan([0.1], [0], [1])                 # scan before load
+        sc.load(prob)
+        T, iA, ix, ia, ns = sc.scan([], [], [])      # empty batch
+        assert len(T) == 0
+        with pytest.raises(BlmxError):
+            sc.set_option('group', 3)
+        bad = ScanProblem(prob.genpos, np.full_like(prob.cls, 10 ** 6), prob.G, prob.SP, prob.A, prob.n_x, prob.n_a)
+        with pytest.raises(BlmxError):
+            sc.load(bad)
+    # a problem with no sites at all
+    empty = ScanProblem(np.zeros(0), np.zeros(0, np.int32), prob.G, prob.SP, prob.A, prob.n_x, prob.n_a)
+    with Scanner(device=0).load(empty) as sc:
+        T, iA, ix, ia, ns = sc.scan([0.5, 1.0], [0, 0], [10, -1])
+        assert np.all(T == 0) and np.all(iA == -1) and np.all(ns == 0)
+
+
+def test_unsorted_genpos_and_duplicates():
+    """The reference never checks that the input is sorted; distance pruning must switch off."""
+    data, prob, order = _problem('synth_dup_genpos_B2')
+    from ballermixplus_b200.native import ScanProblem
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(prob.genpos))
+    shuffled = ScanProblem(prob.genpos[perm], prob.cls[perm], prob.G, prob.SP, prob.A, prob.n_x, prob.n_a)
+    n = len(perm)
+    t = prob.genpos[rng.integers(0, n, size=40)]
+    lo = rng.integers(0, n // 2, size=40)
+    hi = lo + rng.integers(0, n // 2, size=40)
+    for p in (prob, shuffled):
+        T, iA, ix, ia, ns, bad = _check_against_oracle(p, t, lo, hi)
+        assert not bad
+
+
+def test_large_xa_grid_needs_several_passes():
+    """n_x * n_a > 512: the kernel sweeps the (x, a) grid in blocks of 512."""
+    from ballermixplus_b200.native import ScanProblem
+    data, prob, order = _problem('ex2_B0_s5')
+    reps = 3                                          # 510 * 3 = 1530 grid points
+    SP = np.concatenate([prob.SP * (1 + 1e-3 * r) for r in range(reps)])
+    big = ScanProblem(prob.genpos, prob.cls, prob.G, SP, prob.A, prob.n_x * reps, prob.n_a)
+    c = np.arange(0, data.numSites, 9)
+    t, lo, hi = data.genPos[c], np.zeros(len(c), np.int64), np.full(len(c), data.numSites - 1, np.int64)
+    T, iA, ix, ia, ns, bad = _check_against_oracle(big, t, lo, hi)
+    assert not bad
+
+
+def test_extreme_tables_stay_in_range():
+    """Probabilities that underflow, huge likelihood ratios and alpha -> 1: the exponent
+    bookkeeping must keep every product in range (T up to several thousand)."""
+    from ballermixplus_b200.native import ScanProblem
+    rng = np.random.default_rng(11)
+    n_sites, C, n_xa = 4000, 6, 40
+    g = np.sort(rng.random(n_sites)) * 1e-3
+    g[100:104] = g[100] + np.array([0, 1e-15, 2e-15, 1e-13])      # alpha within 1e-11 of 1
+    cls = rng.integers(0, C, size=n_sites).astype(np.int32)
+    G = np.array([0.5, 0.2, 0.1, 0.1, 0.05, 0.05])
+    SP = rng.random((n_xa, C)) * G * 2
+    SP[3] = G * 50.                       # every factor up to 50: T ~ 2*n*log(50) overflows a double product
+    SP[5, :] = G * 1e-300                 # D = -1 (+1e-300)
+    SP[6, 2] = 0.                         # exact zero: T = -inf for windows touching class 2 at alpha = 1
+    SP[7] = G * 1e12
+    prob = ScanProblem(g, cls, G, SP, [50., 2000., 1e5, 1e7], 8, 5)
+    c = np.array([0, 100, 101, 103, 2000, 3999])
+    t = g[c]
+    lo, hi = np.zeros(len(c), np.int64), np.full(len(c), n_sites - 1, np.int64)
+    for group in (1, 4):
+        T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, group=group)
+        assert not bad
+        assert np.all(np.isfinite(T)) and T.max() > 2000.
+
+
+def test_synthetic_n200_against_oracle_sample():
+    """cfg4-shaped synthetic input (n = 200, 200 classes, 100 A x 510 grid) at a size the C oracle
+    finishes in seconds, plus size-independent properties on the full centre list."""
+    import bench
+    from ballermixplus_b200.native import Scanner
+    chrom = bench.make_chromosome(20000, seed=12345)
+    prob, grid_shape = bench.make_problem([chrom])[0], None
+    n = len(prob.genpos)
+    rng = np.random.default_rng(2)
+    c = np.sort(rng.choice(n, size=24, replace=False))
+    t, lo, hi = prob.genpos[c], np.zeros(len(c), np.int64), np.full(len(c), n - 1, np.int64)
+    T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi)
+    assert not bad
+    # properties at full size: all centres, (1) group 1 == group 4, (2) results do not depend on batching,
+    # (3) a window cut at the alpha reach of the smallest A changes nothing
+    call = np.arange(0, n, 40)
+    ta, loa, hia = prob.genpos[call], np.zeros(len(call), np.int64), np.full(len(call), n - 1, np.int64)
+    with Scanner(device=0, group=4).load(prob) as sc:
+        r4 = sc.scan(ta, loa, hia)
+        reach = 18.420680743952367 / prob.A.min() * 1.01
+        lo2 = np.searchsorted(prob.genpos, ta - reach, 'left')
+        hi2 = np.searchsorted(prob.genpos, ta + reach, 'right') - 1
+        rcut = sc.scan(ta, lo2, hi2)
+        sc.set_option('batch', 100)
+        rb = sc.scan(ta, loa, hia)
+    with Scanner(device=0, group=1).load(prob) as sc:
+        r1 = sc.scan(ta, loa, hia)
+    for other in (rcut, rb):
+        for a, b in zip(r4, other):
+            assert np.array_equal(a, b)
+    assert np.allclose(r4[0], r1[0], rtol=1e-11, atol=1e-11)
+    for a, b in zip(r4[1:], r1[1:]):
+        assert np.array_equal(a, b)
