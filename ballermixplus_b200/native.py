@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libblmx.so')
+LIB_PATH = os.environ.get('BLMX_LIB') or os.path.join(_HERE, 'libblmx.so')   # BLMX_LIB: tuning builds
 
 #: every symbol include/blmx.h declares (tests check that the library exports them)
 ABI_SYMBOLS = (
