@@ -78,3 +78,20 @@ def gather_rows(rows, counts, rank, world, dist, torch, dst=0):
         return torch.cat([bufs[r][:counts[r]] for r in range(world)], dim=0)
     dist.gather(padded, gather_list=None, dst=dst)
     return None
+
+
+def scan_sharded(genpos, A, t, lo, hi, rank, world, scan_fn, dist, torch):
+    """Scan one sequence's centres on `world` ranks and gather the rows on rank 0.
+
+    `scan_fn(t, lo, hi)` scans a contiguous slice of the centre list on this rank's device and
+    returns torch tensors (T float64, iA, ix, ia, nsites int32) living on that device (the
+    product passes a closure over ``Scanner.scan_device``; CPU tests pass the oracle).
+    Returns the five gathered tensors on rank 0 (in centre order) and None elsewhere.
+    """
+    costs = centre_costs(genpos, t, lo, hi, A)
+    parts = partition(costs, world)
+    counts = [e - b for b, e in parts]
+    b, e = parts[rank]
+    rows = pack_rows(*scan_fn(t[b:e], lo[b:e], hi[b:e]), torch)
+    got = gather_rows(rows, counts, rank, world, dist, torch)
+    return unpack_rows(got, torch) if got is not None else None

@@ -160,10 +160,13 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_sample_size(threads):
-    """Centres for ~20 s of CPU work: the literal port needs ~60 core-seconds per interior centre
-    of the 10 M-site workload (6.6e8 log evaluations), parallelised over (centre, A) tasks."""
-    return max(2, int(round(threads * 0.3)))
+def cpu_sample_size(problems, plans, threads, target_s=15.0):
+    """Centres for about `target_s` seconds of CPU work on this host: time two centres first
+    (an interior centre of the 10 M-site workload is 6.6e8 log evaluations, parallelised over
+    (centre, A) tasks), then scale."""
+    secs, centres, _ = run_cpu_oracle(problems, plans, cpu_sample(problems, plans, 2, threads), threads)
+    per_centre = max(secs / max(centres, 1), 1e-3)
+    return int(min(4096, max(2, round(target_s / per_centre))))
 
 
 def cpu_sample(problems, plans, n_centres, threads):
@@ -207,7 +210,7 @@ def reference_arm(opt, rank):
     stride = max(1, BASE_STRIDE // opt.gpus)
     plans = plan_centres(problems, stride)
     n_grid = problems[0].n_x * problems[0].n_a * len(problems[0].A)
-    per_step = opt.cpu_centres or cpu_sample_size(threads)
+    per_step = opt.cpu_centres or cpu_sample_size(problems, plans, threads, target_s=12.0)
     sample = cpu_sample(problems, plans, per_step, threads)
     for _ in range(opt.warmup):
         run_cpu_oracle(problems, plans, cpu_sample(problems, plans, 1, threads), threads)
@@ -434,7 +437,7 @@ def cuda_arm(opt, rank, world, local_rank):
         }
         if world == 1 and not opt.no_cpu:
             threads = len(os.sched_getaffinity(0))
-            n_cpu = opt.cpu_centres or cpu_sample_size(threads)
+            n_cpu = opt.cpu_centres or cpu_sample_size(problems, plans, threads)
             sample = cpu_sample(problems, plans, n_cpu, threads)
             secs, centres, cpairs = run_cpu_oracle(problems, plans, sample, threads)
             line['cpu_baseline'] = {
