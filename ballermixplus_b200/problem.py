@@ -18,7 +18,9 @@ class GridOrder:
     """The three grids in visiting order, with the Python objects kept for output."""
 
     def __init__(self, grids):
-        self.A, self.x, self.a = grids.scan_order()
+        # list(set(...)) is what the reference's loops iterate (v1:453,473,474); works on the
+        # reference's own Grids object as well as on ours
+        self.A, self.x, self.a = list(set(grids.A)), list(set(grids.x)), list(set(grids.abeta))
 
     @property
     def n_points(self):
@@ -35,14 +37,25 @@ def build_problem(data, neutral, sel, grids):
     """-> (ScanProblem, GridOrder)."""
     order = GridOrder(grids)
     class_k, class_n, cls = site_classes(data.count, data.total)
-    G, P = neutral.class_tables(class_k, class_n)
-    if not (np.array_equal(class_k, sel.class_k) and np.array_equal(class_n, sel.class_n)):
-        raise ValueError('selection tables were built for different data')
+    pairs = list(zip(class_k.tolist(), class_n.tolist()))
+    if hasattr(neutral, 'class_tables'):
+        G, P = neutral.class_tables(class_k, class_n)
+    else:                                   # the reference's NeutralSFS: same dictionaries (v1:271,275)
+        G = np.array([neutral.spect[p] for p in pairs], dtype=np.float64)
+        P = np.array([neutral.sampProps[p[1]] for p in pairs], dtype=np.float64)
+    if hasattr(sel, 'classProbs'):
+        if not (np.array_equal(class_k, sel.class_k) and np.array_equal(class_n, sel.class_n)):
+            raise ValueError('selection tables were built for different data')
+        rows = sel.classProbs
+    else:                                   # the reference's NormalizedBetaBinom: per-site arrays (v1:359)
+        first = np.zeros(len(pairs), dtype=np.int64)
+        first[cls[::-1]] = np.arange(len(cls))[::-1]          # first site of every class
+        rows = {key: np.asarray(v)[first] for key, v in sel.normProbs.items()}
     SP = np.empty((len(order.x) * len(order.a), len(G)), dtype=np.float64)
     r = 0
     for x in order.x:
         for a in order.a:
-            SP[r] = sel.classProbs[(x, a)] * P
+            SP[r] = rows[(x, a)] * P
             r += 1
     prob = ScanProblem(data.genPos, cls, G, SP, np.array([float(v) for v in order.A]),
                        len(order.x), len(order.a))
