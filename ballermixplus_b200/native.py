@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get('BLMX_LIB') or os.path.join(_HERE, 'libblmx.so')   # B
 ABI_SYMBOLS = (
     'blmx_abi_version', 'blmx_last_error', 'blmx_device_count', 'blmx_create', 'blmx_destroy',
     'blmx_load', 'blmx_scan', 'blmx_scan_device', 'blmx_scan_oneshot', 'blmx_set_option',
-    'blmx_last_counters', 'blmx_last_kernel_ms', 'blmx_measure_fp64_peak',
+    'blmx_last_counters', 'blmx_last_counters4', 'blmx_last_kernel_ms', 'blmx_measure_fp64_peak',
 )
 
 
@@ -59,6 +59,7 @@ def lib():
         L.blmx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.blmx_last_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_uint64)]
+        L.blmx_last_counters4.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 4), C.POINTER(C.c_uint64)]
         L.blmx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.blmx_measure_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double),
                                              C.POINTER(C.c_double)]
@@ -115,7 +116,7 @@ class ScanProblem:
 class Scanner:
     """One handle on one device with one problem resident in HBM."""
 
-    def __init__(self, device=0, group=None, batch=None):
+    def __init__(self, device=0, group=None, batch=None, farfield=None):
         self._h = C.c_void_p()
         _check(lib().blmx_create(int(device), C.byref(self._h)))
         self.device = int(device)
@@ -123,6 +124,8 @@ class Scanner:
             self.set_option('group', group)
         if batch is not None:
             self.set_option('batch', batch)
+        if farfield is not None:
+            self.set_option('farfield', farfield)
 
     def set_option(self, name, value):
         _check(lib().blmx_set_option(self._h, name.encode(), int(value)))
@@ -164,6 +167,12 @@ class Scanner:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         _check(lib().blmx_last_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def counters4(self):
+        """(site pairs, singles, far-field moment updates, far-field polynomial terms, launches)."""
+        v, c = (C.c_uint64 * 4)(), C.c_uint64(0)
+        _check(lib().blmx_last_counters4(self._h, C.byref(v), C.byref(c)))
+        return v[0], v[1], v[2], v[3], c.value
 
     def kernel_ms(self):
         """(summed scan-kernel ms, launches) of the most recent scan; needs option timing=1."""

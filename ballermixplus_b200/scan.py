@@ -6,6 +6,7 @@ CUDA library behind include/blmx.h.  ``Scan`` plans all centres of the run first
 (windows.py), sends them to the GPU in one ``blmx_scan`` call and then writes the
 rows with the reference's f-string formatting.
 """
+import os
 from datetime import datetime
 
 import numpy as np
@@ -20,9 +21,12 @@ HEADER = 'physPos\tgenPos\tCLR\tx_hat\ts_hat\tA_hat\tnSites\n'
 class DeviceScan:
     """A problem resident on one GPU plus the grid objects needed to decode results."""
 
-    def __init__(self, InputData, NeutralSFS, NormalizedBetaBinom, Grids, device=0, group=None):
+    def __init__(self, InputData, NeutralSFS, NormalizedBetaBinom, Grids, device=0, group=None,
+                 farfield=None):
         self.problem, self.order = build_problem(InputData, NeutralSFS, NormalizedBetaBinom, Grids)
-        self.scanner = Scanner(device=device, group=group).load(self.problem)
+        if farfield is None and os.environ.get('BLMX_FARFIELD'):
+            farfield = int(os.environ['BLMX_FARFIELD'])
+        self.scanner = Scanner(device=device, group=group, farfield=farfield).load(self.problem)
 
     def run(self, t, lo, hi):
         """-> (T float64[n], iA, ix, ia, nsites int32[n]); indices into the visiting order."""

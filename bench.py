@@ -284,7 +284,7 @@ def cuda_arm(opt, rank, world, local_rank):
     # resident problems + device buffers
     scanners = {}
     for c, _ in mine:
-        scanners[c] = native.Scanner(device=local_rank, group=opt.group).load(problems[c])
+        scanners[c] = native.Scanner(device=local_rank, group=opt.group, farfield=opt.farfield).load(problems[c])
         scanners[c].set_option('timing', 1)
     stream = torch.cuda.current_stream().cuda_stream
     host_in = {c: tuple(np.ascontiguousarray(a[sl]) for a in plans[c]) for c, sl in mine}
@@ -461,6 +461,7 @@ def main():
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--sites', type=int, default=10_000_000, help='informative sites in the synthetic genome')
     ap.add_argument('--group', type=int, default=4, choices=[1, 4])
+    ap.add_argument('--farfield', type=int, default=0, choices=[0, 1], help='power-sum far field (see DESIGN.md)')
     ap.add_argument('--cpu-centres', type=int, default=0, help='centres in the CPU sample (default: one per thread)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     opt = ap.parse_args()

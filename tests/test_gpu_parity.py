@@ -22,9 +22,11 @@ def run_cli(argv, out):
         return fh.read().splitlines(keepends=True)
 
 
+@pytest.mark.parametrize('farfield', [0, 1])
 @pytest.mark.parametrize('name', sorted(CASES))
-def test_cli_scan_matches_reference_golden(name, tmp_path):
+def test_cli_scan_matches_reference_golden(name, farfield, tmp_path, monkeypatch):
     """Whole runs of the drop-in CLI (all rows) against the reference's output files."""
+    monkeypatch.setenv('BLMX_FARFIELD', str(farfield))
     argv, gold = CASES[name]
     lines = run_cli(argv, str(tmp_path / 'out.txt'))
     n, same, worst, ties = util.compare_scan(lines, gold, rtol=1e-9, max_near_ties=NEAR_TIES.get(name, 0))
@@ -40,10 +42,10 @@ def _problem(name):
     return data, prob, order
 
 
-def _check_against_oracle(prob, t, lo, hi, group=None, batch=None, rtol=1e-9):
+def _check_against_oracle(prob, t, lo, hi, group=None, batch=None, rtol=1e-9, farfield=None):
     from oracle import oracle_c
     from ballermixplus_b200.native import Scanner
-    with Scanner(device=0, group=group, batch=batch).load(prob) as sc:
+    with Scanner(device=0, group=group, batch=batch, farfield=farfield).load(prob) as sc:
         T, iA, ix, ia, ns = sc.scan(t, lo, hi)
         pairs, _ = sc.counters()
     rT, rA, rxa, rn, rpairs = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t, lo, hi)
@@ -54,8 +56,8 @@ def _check_against_oracle(prob, t, lo, hi, group=None, batch=None, rtol=1e-9):
     return T, iA, ix, ia, ns, bad
 
 
-@pytest.mark.parametrize('group', [1, 4])
-def test_ragged_windows_and_batches(group):
+@pytest.mark.parametrize('group,farfield', [(1, 0), (4, 0), (4, 1)])
+def test_ragged_windows_and_batches(group, farfield):
     """Random, ragged, empty and out-of-range windows; small batches force several launches."""
     data, prob, order = _problem('Example2_B2')
     rng = np.random.default_rng(3)
@@ -68,7 +70,7 @@ def test_ragged_windows_and_batches(group):
     lo[::11] = hi[::11] + 5                          # empty windows
     lo[::13] = -50                                   # clamped by the library
     hi[::17] = data.numSites + 100
-    T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, group=group, batch=64)
+    T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, group=group, batch=64, farfield=farfield)
     assert not bad
     empty = np.flatnonzero(lo > hi)
     assert np.all(T[empty] == 0) and np.all(iA[empty] == -1) and np.all(ns[empty] == 0)
@@ -121,8 +123,9 @@ def test_unsorted_genpos_and_duplicates():
     lo = rng.integers(0, n // 2, size=40)
     hi = lo + rng.integers(0, n // 2, size=40)
     for p in (prob, shuffled):
-        T, iA, ix, ia, ns, bad = _check_against_oracle(p, t, lo, hi)
-        assert not bad
+        for ff in (0, 1):
+            T, iA, ix, ia, ns, bad = _check_against_oracle(p, t, lo, hi, farfield=ff)
+            assert not bad
 
 
 def test_large_xa_grid_needs_several_passes():
@@ -157,8 +160,8 @@ def test_extreme_tables_stay_in_range():
     c = np.array([0, 100, 101, 103, 2000, 3999])
     t = g[c]
     lo, hi = np.zeros(len(c), np.int64), np.full(len(c), n_sites - 1, np.int64)
-    for group in (1, 4):
-        T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, group=group)
+    for group, ff in ((1, 0), (4, 0), (4, 1)):
+        T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, group=group, farfield=ff)
         assert not bad
         assert np.all(np.isfinite(T)) and T.max() > 2000.
 
@@ -176,6 +179,9 @@ def test_synthetic_n200_against_oracle_sample():
     t, lo, hi = prob.genpos[c], np.zeros(len(c), np.int64), np.full(len(c), n - 1, np.int64)
     T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi)
     assert not bad
+    Tf, *_rest, badf = _check_against_oracle(prob, t, lo, hi, farfield=1)
+    assert not badf
+    assert np.max(np.abs(Tf - T)) <= 1e-11 * max(1., np.max(np.abs(T)))
     # properties at full size: all centres, (1) group 1 == group 4, (2) results do not depend on batching,
     # (3) a window cut at the alpha reach of the smallest A changes nothing
     call = np.arange(0, n, 40)
@@ -190,6 +196,13 @@ def test_synthetic_n200_against_oracle_sample():
         rb = sc.scan(ta, loa, hia)
     with Scanner(device=0, group=1).load(prob) as sc:
         r1 = sc.scan(ta, loa, hia)
+    with Scanner(device=0, group=4, farfield=1).load(prob) as sc:
+        rf = sc.scan(ta, loa, hia)
+        far = sc.counters4()
+    assert far[2] > 0 and far[3] > 0                      # the far field was actually used
+    assert np.allclose(r4[0], rf[0], rtol=1e-11, atol=1e-11)
+    for a, b in zip(r4[1:], rf[1:]):
+        assert np.array_equal(a, b)
     for other in (rcut, rb):
         for a, b in zip(r4, other):
             assert np.array_equal(a, b)
