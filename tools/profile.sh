@@ -5,7 +5,7 @@
 # gpurun_out/<tag>_prof.ncu-rep (ncu --set full of two scan_kernel launches of the timed step).
 set -u
 tag=${1:-r1}
-cmd="python bench.py --sites 1000000 --steps 1 --warmup 3 --no-cpu"
+cmd="python bench.py --sites 1000000 --steps 1 --warmup 3 --no-cpu ${BENCH_ARGS:-}"
 mkdir -p gpurun_out
 $cmd > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
