@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get('BLMX_LIB') or os.path.join(_HERE, 'libblmx.so')   # B
 ABI_SYMBOLS = (
     'blmx_abi_version', 'blmx_last_error', 'blmx_device_count', 'blmx_create', 'blmx_destroy',
     'blmx_load', 'blmx_scan', 'blmx_scan_device', 'blmx_scan_oneshot', 'blmx_set_option',
-    'blmx_last_counters', 'blmx_last_counters4', 'blmx_last_kernel_ms', 'blmx_measure_fp64_peak',
+    'blmx_last_counters', 'blmx_last_counters6', 'blmx_last_kernel_ms', 'blmx_measure_fp64_peak',
 )
 
 
@@ -59,7 +59,7 @@ def lib():
         L.blmx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.blmx_last_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_uint64)]
-        L.blmx_last_counters4.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 4), C.POINTER(C.c_uint64)]
+        L.blmx_last_counters6.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 6), C.POINTER(C.c_uint64)]
         L.blmx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.blmx_measure_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double),
                                              C.POINTER(C.c_double)]
@@ -168,11 +168,12 @@ class Scanner:
         _check(lib().blmx_last_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
-    def counters4(self):
-        """(site pairs, singles, far-field moment updates, far-field polynomial terms, launches)."""
-        v, c = (C.c_uint64 * 4)(), C.c_uint64(0)
-        _check(lib().blmx_last_counters4(self._h, C.byref(v), C.byref(c)))
-        return v[0], v[1], v[2], v[3], c.value
+    def counters_all(self):
+        """dict of the work counters of the most recent scan (see blmx_last_counters6)."""
+        v, c = (C.c_uint64 * 6)(), C.c_uint64(0)
+        _check(lib().blmx_last_counters6(self._h, C.byref(v), C.byref(c)))
+        return {'pairs': v[0], 'single': v[1], 'far_updates': v[2], 'far_terms': v[3], 'far_sites': v[4],
+                'launches': c.value}
 
     def kernel_ms(self):
         """(summed scan-kernel ms, launches) of the most recent scan; needs option timing=1."""

@@ -43,6 +43,15 @@ FLOP_SINGLE = 3.0          # 1 + alpha*D (FMA) and the running product (MUL), pe
 FLOP_GROUPED = 2.25        # four sites: 4 FMA (quartic in D) + 1 MUL
 FLOP_EXP = 34.0            # alpha = exp(-A*|g - t|): once per (centre, A, site)
 FLOP_LOG = 47.0 + 3.0      # one log + exponent fold-in per (centre, A, grid point)
+FLOP_MOMENT = 2.0          # far field: alpha^m (MUL) added to S_m (ADD), per site and moment
+FLOP_POLY = 2.0            # far field: one Horner FMA per polynomial term and grid point
+
+
+def algorithmic_flops(cnt, n_xa, n_items):
+    """FP64 flops the formulation needs for the work the kernel's own counters report."""
+    grouped = cnt['pairs'] - cnt['single'] - cnt['far_sites']
+    return (n_xa * (FLOP_SINGLE * cnt['single'] + FLOP_GROUPED * grouped) + FLOP_EXP * cnt['pairs']
+            + FLOP_MOMENT * cnt['far_updates'] + FLOP_POLY * n_xa * cnt['far_terms'] + FLOP_LOG * n_xa * n_items)
 
 
 # ------------------------------------------------------------------------ synthetic data
@@ -320,10 +329,17 @@ def cuda_arm(opt, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = 0.0
-    kernel_launches = 0
-    lib_launches = 0
-    pairs = single = 0
+    def collect():
+        """Per-launch kernel events and work counters of the LAST step, summed over this rank's scanners."""
+        tot = {'pairs': 0, 'single': 0, 'far_updates': 0, 'far_terms': 0, 'far_sites': 0, 'launches': 0}
+        k_ms, k_n = 0.0, 0
+        for c, _ in mine:
+            kms, kn = scanners[c].kernel_ms()
+            k_ms += kms; k_n += kn
+            for key, v in scanners[c].counters_all().items():
+                tot[key] += v
+        return tot, k_ms, k_n
+
     sync_all()
     e0.record()
     for _ in range(opt.steps):
@@ -332,12 +348,26 @@ def cuda_arm(opt, rank, world, local_rank):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    for c, _ in mine:                        # per-launch events of the LAST step, counters likewise
-        kms, kn = scanners[c].kernel_ms()
-        kernel_ms += kms; kernel_launches += kn
-        a, b, l = scanners[c].counters_full()
-        pairs += a; single += b; lib_launches += l
+    cnt, kernel_ms, kernel_launches = collect()
+    pairs, single, lib_launches = cnt['pairs'], cnt['single'], cnt['launches']
     clocks = sampler.stop() if rank == 0 else None
+
+    # the same workload with every site evaluated directly (option farfield = 0): the FP64-bound kernel
+    direct = None
+    if opt.farfield and world == 1:
+        for c, _ in mine:
+            scanners[c].set_option('farfield', 0)
+        scan_resident()
+        sync_all()
+        e0.record()
+        scan_resident()
+        e1.record()
+        sync_all()
+        d_ms = e0.elapsed_time(e1)
+        d_cnt, d_kms, d_kn = collect()
+        direct = (d_ms, d_cnt, d_kms, d_kn)
+        for c, _ in mine:
+            scanners[c].set_option('farfield', 1)
     if world > 1:
         tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -391,8 +421,7 @@ def cuda_arm(opt, rank, world, local_rank):
 
         peak_tf, peak_mhz = native.measure_fp64_peak(local_rank, 0.5)
         n_items = n_mine * n_A
-        grouped = pairs - single
-        flops = n_xa * (FLOP_SINGLE * single + FLOP_GROUPED * grouped) + FLOP_EXP * pairs + FLOP_LOG * n_xa * n_items
+        flops = algorithmic_flops(cnt, n_xa, n_items)
         k_s = kernel_ms * 1e-3
         achieved = flops / k_s / 1e12 if k_s > 0 else None
         table_bytes = 8.0 * n_xa * problems[0].G.shape[0] * n_items          # D rows a warp may touch
@@ -419,7 +448,8 @@ def cuda_arm(opt, rank, world, local_rank):
             'gpu_launches': int(launches_all * opt.steps),
             'clocks': clocks,
             'roofline': {
-                'bound': 'fp64', 'kernel': 'scan_kernel<16,%d>' % opt.group, 'achieved': achieved,
+                'bound': 'fp64', 'kernel': 'scan_kernel<16,%d,%s>' % (opt.group, 'far' if opt.farfield else 'direct'),
+                'achieved': achieved,
                 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved and peak_tf else None,
                 'peak_source': 'measured live: register-resident DFMA loop (blmx_measure_fp64_peak); '
                                'MEASURED_PEAKS.json has no FP64 entry',
@@ -427,7 +457,7 @@ def cuda_arm(opt, rank, world, local_rank):
                 'frac_of_nominal': (achieved / FP64_NOMINAL_TFLOPS) if achieved else None,
                 'kernel_ms_per_launch': kernel_ms / max(1, kernel_launches), 'launches_timed': kernel_launches,
                 'algorithmic_flops_per_launch': flops / max(1, kernel_launches),
-                'sites_single_frac': single / max(1, pairs),
+                'sites_single_frac': single / max(1, pairs), 'sites_far_frac': cnt['far_sites'] / max(1, pairs),
                 'traffic': traffic,
                 'hbm': {'algorithmic_bytes_per_launch': (site_bytes + table_bytes) / max(1, kernel_launches),
                         'achieved_gbs': (site_bytes + table_bytes) / k_s / 1e9 if k_s > 0 else None,
@@ -435,6 +465,19 @@ def cuda_arm(opt, rank, world, local_rank):
                         'note': 'upper bound (every class row counted); the path is FP64-bound'},
             },
         }
+        line['mode'] = ('farfield: far sites through power sums of alpha (DESIGN.md §3.5)' if opt.farfield
+                        else 'direct: every site evaluated per grid point')
+        if direct is not None:
+            d_ms, d_cnt, d_kms, d_kn = direct
+            d_flops = algorithmic_flops(d_cnt, n_xa, n_items)
+            d_ach = d_flops / (d_kms * 1e-3) / 1e12
+            line['direct'] = {
+                'value': total_centres * n_grid / (d_ms * 1e-3), 'unit': 'centre*gridpoint/s', 'ms_per_step': d_ms,
+                'roofline': {'bound': 'fp64', 'kernel': 'scan_kernel<16,%d,direct>' % opt.group, 'achieved': d_ach,
+                             'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': d_ach / peak_tf,
+                             'kernel_ms_per_launch': d_kms / max(1, d_kn), 'launches_timed': d_kn,
+                             'algorithmic_flops_per_launch': d_flops / max(1, d_kn)},
+                'note': 'same step with option farfield = 0 (one warm-up + one timed step)'}
         if world == 1 and not opt.no_cpu:
             threads = len(os.sched_getaffinity(0))
             n_cpu = opt.cpu_centres or cpu_sample_size(problems, plans, threads)
@@ -461,7 +504,8 @@ def main():
     ap.add_argument('--impl', default='cuda', choices=['cuda', 'reference'])
     ap.add_argument('--sites', type=int, default=10_000_000, help='informative sites in the synthetic genome')
     ap.add_argument('--group', type=int, default=4, choices=[1, 4])
-    ap.add_argument('--farfield', type=int, default=0, choices=[0, 1], help='power-sum far field (see DESIGN.md)')
+    ap.add_argument('--farfield', type=int, default=1, choices=[0, 1],
+                    help='1 (default): far sites enter through power sums; 0: every site evaluated directly')
     ap.add_argument('--cpu-centres', type=int, default=0, help='centres in the CPU sample (default: one per thread)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     opt = ap.parse_args()

@@ -122,8 +122,9 @@ int blmx_scan_oneshot(int device, const blmx_problem *p, int64_t n_centres, cons
  * Options (before or after load):
  *   "group"      1 = one FMA+MUL per site-evaluation; 4 = far sites are folded four
  *                at a time into a quartic in D (default)
- *   "farfield"   1 = sites of a class with alpha*max|D| <= theta contribute through power sums
- *                of alpha (series of log(1 + alpha D), truncation < 2^-70 per site); needs group 4
+ *   "farfield"   1 (default) = sites of a class with alpha*max|D| <= theta contribute through
+ *                power sums of alpha (series of log(1 + alpha D), truncation < 2^-70 per site;
+ *                needs group 4); 0 = every site is evaluated per grid point
  *   "batch"      centres per kernel launch (scratch = batch * n_A * 16 bytes)
  *   "timing"     1 = record CUDA events around every scan kernel (see blmx_last_kernel_ms)
  */
@@ -138,10 +139,10 @@ int blmx_set_option(blmx_handle *h, const char *name, int64_t value);
  */
 int blmx_last_counters(blmx_handle *h, uint64_t *site_pairs, uint64_t *single_pairs,
                        uint64_t *launches);
-/* All four work counters: [0] site_pairs, [1] single_pairs, [2] far-field moment updates
- * (one DMUL + one DADD each), [3] far-field polynomial terms summed over class visits
- * (one DFMA per term and grid point). */
-int blmx_last_counters4(blmx_handle *h, uint64_t *four, uint64_t *launches);
+/* All work counters: [0] site_pairs, [1] single_pairs, [2] far-field moment updates (one
+ * DMUL + one DADD each), [3] far-field polynomial terms summed over class visits (one DFMA
+ * per term and grid point), [4] site pairs that entered through the far field, [5] reserved. */
+int blmx_last_counters6(blmx_handle *h, uint64_t *six, uint64_t *launches);
 
 /*
  * With option "timing" = 1 the library records a CUDA event pair around every scan-kernel
