@@ -18,8 +18,13 @@ import sys
 
 import numpy as np
 
+from . import fastio
+
 
 def _read_xn(infile):
+    fast = fastio.read_sites(infile, True, 1.0, strict_columns=True)     # C++ reader; None -> the loop below
+    if fast is not None:
+        return fast[2], fast[3]
     xs, ns = [], []
     with open(infile, 'r') as fh:
         next(fh, None)

@@ -22,6 +22,8 @@ import sys
 
 import numpy as np
 
+from . import fastio
+
 _MSG_TRANSLATE = ('Input includes different variant counts despite choosing not to use allele '
                   'frequencies (with --noFreq). All sites with counts smaller than substitutions '
                   'will be considered as polymorphic. All sites with identical counts as sample '
@@ -35,6 +37,9 @@ def read_site_table(infile, use_phys, Rrate):
 
     Returns (position int64[N], genPos float64[N], k int64[N], n int64[N]).
     """
+    fast = fastio.read_sites(infile, use_phys, Rrate)      # C++ reader; None -> the loop below
+    if fast is not None:
+        return fast
     pos, gen, kk, nn = [], [], [], []
     col = 0 if use_phys else 1
     with open(infile, 'r') as fh:

@@ -11,7 +11,7 @@ from datetime import datetime
 
 import numpy as np
 
-from . import windows
+from . import fastio, windows
 from .native import Scanner
 from .problem import build_problem
 
@@ -63,15 +63,29 @@ def calcBaller(window_indice, testSite, InputData, NeutralSFS, NormalizedBetaBin
 
 
 def format_rows(plan, order, T, iA, ix, ia, ns):
-    """Output lines for a plan and its results (v1:535,540,574,591,607)."""
+    """Output lines for a plan and its results (v1:535,540,574,591,607), formatted by Python
+    exactly as the reference's f-strings do."""
     lines = []
+    f0, f1 = plan.f0, plan.f1
     for j in range(len(plan)):
         if plan.gap[j]:
-            lines.append(plan.f0[j])
+            lines.append(f0[j])
             continue
         Tm, xh, ah, Ah, w = order.decode(T[j], iA[j], ix[j], ia[j], ns[j])
-        lines.append(f'{plan.f0[j]}\t{plan.f1[j]}\t{Tm}\t{xh}\t{ah}\t{Ah}\t{w}\n')
+        lines.append(f'{f0[j]}\t{f1[j]}\t{Tm}\t{xh}\t{ah}\t{Ah}\t{w}\n')
     return lines
+
+
+def write_scan(outfile, plan, order, T, iA, ix, ia, ns):
+    """Write the output file: the C++ writer for site-centred scans without gap rows (same bytes,
+    tests/test_fastio.py), the Python formatter otherwise."""
+    if plan.site_phys is not None and not np.any(plan.gap):
+        texts = [[f'{v}' for v in grid] for grid in (order.A, order.x, order.a)]
+        if fastio.write_rows(outfile, HEADER, plan.site_phys, plan.site_gen, T, iA, ix, ia, ns, *texts):
+            return
+    with open(outfile, 'w') as scores:
+        scores.write(HEADER)
+        scores.writelines(format_rows(plan, order, T, iA, ix, ia, ns))
 
 
 class Scan:
@@ -90,9 +104,7 @@ class Scan:
             if len(live):
                 T[live], iA[live], ix[live], ia[live], ns[live] = dev.run(t[live], lo[live], hi[live])
             self.results = (T, iA, ix, ia, ns)
-            with open(outfile, 'w') as scores:
-                scores.write(HEADER)
-                scores.writelines(format_rows(plan, dev.order, T, iA, ix, ia, ns))
+            write_scan(outfile, plan, dev.order, T, iA, ix, ia, ns)
         finally:
             dev.close()
         print(f'{datetime.now()}. Scan finished.')

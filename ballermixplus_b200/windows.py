@@ -15,21 +15,44 @@ import numpy as np
 
 
 class ScanPlan:
+    """Rows of one scan.  Site-centred modes keep the two leading output columns as the numpy
+    values the reference prints (``site_phys`` int64, ``site_gen`` float64) so that a whole
+    genome is never formatted row by row in Python; ``f0``/``f1`` give them as text on demand."""
+
     def __init__(self):
         self.t = []          # float64 test positions
         self.lo = []
         self.hi = []
-        self.f0 = []         # first output column (physPos) as text
-        self.f1 = []         # second output column (genPos) as text
+        self._f0 = []        # first output column (physPos) as text
+        self._f1 = []        # second output column (genPos) as text
         self.gap = []        # --noCenter gap rows (already complete in f0)
+        self.site_phys = None
+        self.site_gen = None
 
     def add(self, t, lo, hi, f0, f1):
         self.t.append(t); self.lo.append(lo); self.hi.append(hi)
-        self.f0.append(f0); self.f1.append(f1); self.gap.append(False)
+        self._f0.append(f0); self._f1.append(f1); self.gap.append(False)
+
+    def set_sites(self, data, idx):
+        """All rows are centred on the sites `idx` (a numpy index array)."""
+        self.site_phys = np.ascontiguousarray(data.position[idx], dtype=np.int64)
+        self.site_gen = np.ascontiguousarray(data.genPos[idx], dtype=np.float64)
+
+    @property
+    def f0(self):
+        if self.site_phys is not None:
+            return [f'{v}' for v in self.site_phys]
+        return self._f0
+
+    @property
+    def f1(self):
+        if self.site_gen is not None:
+            return [f'{v}' for v in self.site_gen]
+        return self._f1
 
     def add_gap(self, line):
         self.t.append(0.); self.lo.append(0); self.hi.append(-1)
-        self.f0.append(line); self.f1.append(''); self.gap.append(True)
+        self._f0.append(line); self._f1.append(''); self.gap.append(True)
 
     def arrays(self):
         return (np.array(self.t, dtype=np.float64), np.array(self.lo, dtype=np.int64),
@@ -47,12 +70,11 @@ def plan_alpha(data, s):
     N = data.numSites
     plan = ScanPlan()
     idx = np.arange(0, N, step)
-    plan.t = data.genPos[idx].tolist()
-    plan.lo = [0] * len(idx)
-    plan.hi = [N - 1] * len(idx)
-    plan.f0 = [f'{v}' for v in data.position[idx]]
-    plan.f1 = [f'{v}' for v in data.genPos[idx]]
-    plan.gap = [False] * len(idx)
+    plan.t = data.genPos[idx]
+    plan.lo = np.zeros(len(idx), np.int64)
+    plan.hi = np.full(len(idx), N - 1, np.int64)
+    plan.gap = np.zeros(len(idx), bool)
+    plan.set_sites(data, idx)
     return plan
 
 
@@ -63,11 +85,14 @@ def plan_site_based(data, r, s):
     N = data.numSites
     plan = ScanPlan()
     i = 0
+    centres = []
     while i < N:
         c = int(i)
         w = np.arange(max(0, i - r), min(N - 1, i + r + 1) + 1, dtype=int)   # as v1:588-589
-        plan.add(data.genPos[c], int(w[0]), int(w[-1]), f'{data.position[c]}', f'{data.genPos[c]}')
+        plan.add(data.genPos[c], int(w[0]), int(w[-1]), None, None)
+        centres.append(c)
         i += s
+    plan.set_sites(data, np.array(centres, dtype=np.int64))
     return plan
 
 
@@ -93,7 +118,8 @@ def plan_fixsize_site_center(data, w, s):
             print(start, si, end, ei)
             raise SystemExit(1)                                          # v1:566-570
         ei = min(ei, N - 1)
-        plan.add(data.genPos[i], si, ei, f'{ts}', f'{data.genPos[i]}')
+        plan.add(data.genPos[i], si, ei, None, None)
+    plan.set_sites(data, np.arange(0, N, step))
     return plan
 
 
