@@ -465,7 +465,7 @@ def cuda_arm(opt, rank, world, local_rank):
                         'note': 'upper bound (every class row counted); the path is FP64-bound'},
             },
         }
-        line['mode'] = ('farfield: far sites through power sums of alpha (DESIGN.md §3.5)' if opt.farfield
+        line['mode'] = ('farfield: far sites through power sums of alpha (DESIGN.md §3.4)' if opt.farfield
                         else 'direct: every site evaluated per grid point')
         if direct is not None:
             d_ms, d_cnt, d_kms, d_kn = direct

@@ -53,7 +53,7 @@ def main():
     os.makedirs(dst, exist_ok=True)
     out = [f'# ncu summary `{tag}`', '',
            'Produced by `tools/profile.sh` on a B200 (gpurun) and `tools/summarise_profile.py` here.',
-           'Command profiled: `python bench.py --sites 1000000 --steps 1 --warmup 3 --no-cpu`',
+           'Command profiled: `python bench.py --sites 1000000 --steps 1 --warmup 3 --no-cpu ' + ' '.join(sys.argv[2:]) + '`',
            '(ncu launch times are cold-cache and serialised: compare shares, not absolutes).', '']
 
     # ---- launch list
