@@ -52,6 +52,9 @@ CF_B1 = D + "HC_CEU_Neut_config_for_B1.txt"
 MIXN = D + "synth_mixed_n.txt"
 MIXN_SP = "gen/synth_mixed_n_spect.txt"
 DUPS = D + "synth_dup_genpos.txt"
+N200 = D + "synth_n200.txt"
+N200_SP = "gen/synth_n200_spect.txt"
+LIST_A_100 = ",".join(str(float(a)) for a in range(1000, 11000, 100))     # == --rangeA 1000,10900,100
 
 # name -> (argv after the script name, output file relative to tests/golden)
 # scan cases write -o gen/<name>.txt ; helper cases write --spect gen/<name>.txt
@@ -65,6 +68,7 @@ CASES = {
     "config_ex1_B1": (["-i", EX1, "--getConfig", "--spect", "gen/config_ex1_B1.txt"], "gen/config_ex1_B1.txt"),
     "config_ex2_B1": (["-i", EX2, "--getConfig", "--spect", "gen/config_ex2_B1.txt"], "gen/config_ex2_B1.txt"),
     "synth_mixed_n_spect": (["-i", MIXN, "--getSpect", "--spect", MIXN_SP], MIXN_SP),
+    "synth_n200_spect": (["-i", N200, "--getSpect", "--spect", N200_SP], N200_SP),
     # --- scans not pinned by a shipped golden ---
     "ex2_B0_s5": (["-i", EX2NS, "--spect", SP_B0, "--noSub", "-s", "5", "-o", "gen/ex2_B0_s5.txt"], "gen/ex2_B0_s5.txt"),
     "ex2_B0_dropsub_s20": (["-i", EX2, "--spect", SP_B0, "--noSub", "-s", "20", "-o", "gen/ex2_B0_dropsub_s20.txt"], "gen/ex2_B0_dropsub_s20.txt"),
@@ -82,10 +86,14 @@ CASES = {
     "ex1M_B2maf_s80": (["-i", EX1M, "--spect", SP_B2M, "--MAF", "-s", "80", "-o", "gen/ex1M_B2maf_s80.txt"], "gen/ex1M_B2maf_s80.txt"),
     "ex1_B1_s80": (["-i", EX1, "--spect", CF_B1, "--noFreq", "-s", "80", "-o", "gen/ex1_B1_s80.txt"], "gen/ex1_B1_s80.txt"),
     "synth_mixed_n_B2_s20": (["-i", MIXN, "--spect", MIXN_SP, "-s", "20", "-o", "gen/synth_mixed_n_B2_s20.txt"], "gen/synth_mixed_n_B2_s20.txt"),
+    # the bench workload's shape (n = 200, 100-point A grid, --usePhysPos --rec 1e-8) at a size the
+    # reference finishes in minutes: 5 centres x 51 000 grid points
+    "synth_n200_B2_s700": (["-i", N200, "--spect", N200_SP, "--usePhysPos", "--rec", "1e-8", "--listA", LIST_A_100,
+                             "-s", "700", "-o", "gen/synth_n200_B2_s700.txt"], "gen/synth_n200_B2_s700.txt"),
     "synth_dup_genpos_B2": (["-i", DUPS, "--spect", SP_B2, "--fixX", "0.2", "--listA", "100,1000,1e6,1e8", "-o", "gen/synth_dup_genpos_B2.txt"], "gen/synth_dup_genpos_B2.txt"),
 }
 # cases whose inputs are produced by another case
-DEPENDS = {"synth_mixed_n_B2_s20": "synth_mixed_n_spect"}
+DEPENDS = {"synth_mixed_n_B2_s20": "synth_mixed_n_spect", "synth_n200_B2_s700": "synth_n200_spect"}
 
 
 def copy_reference_data():
@@ -125,6 +133,24 @@ def make_synthetic_inputs():
             fh.write(f"{p}\t{float(g)!r}\t{kk}\t50\n")
 
 
+def make_n200_input():
+    """The bench generator (n = 200, P(sub) = 0.7, P(k) ~ 1/k, 70 nt spacing), 3000 sites."""
+    rng = np.random.default_rng(777)
+    n_sites, n = 3000, 200
+    pos = np.sort(rng.choice(n_sites * 70 - 1, size=n_sites, replace=False)) + 1
+    is_sub = rng.random(n_sites) < 0.7
+    w = 1. / np.arange(1, n)
+    k = np.where(is_sub, n, rng.choice(np.arange(1, n), size=n_sites, p=w / w.sum()))
+    # a footprint of balancing selection around site 1400 (otherwise every row is the all-zero row):
+    # within 6 kb most sites become polymorphisms at intermediate frequency
+    near = np.abs(pos - pos[1400]) < 6000
+    k = np.where(near & (rng.random(n_sites) < 0.8), rng.integers(70, 131, size=n_sites), k)
+    with open(os.path.join(HERE, N200), "w") as fh:
+        fh.write("physPos\tgenPos\tx\tn\n")
+        for p, kk in zip(pos, k):
+            fh.write(f"{p}\t{float(p * 1e-8)!r}\t{kk}\t{n}\n")
+
+
 def run_case(name):
     argv, out = CASES[name]
     t0 = time.time()
@@ -141,6 +167,7 @@ def main():
     opt = ap.parse_args()
     copy_reference_data()
     make_synthetic_inputs()
+    make_n200_input()
     names = opt.only or list(CASES)
     first = [n for n in names if n in DEPENDS.values()]
     rest = [n for n in names if n not in first]

@@ -210,3 +210,60 @@ def test_synthetic_n200_against_oracle_sample():
     assert np.allclose(r4[0], r1[0], rtol=1e-11, atol=1e-11)
     for a, b in zip(r4[1:], r1[1:]):
         assert np.array_equal(a, b)
+
+
+def _cli_vs_oracle(argv, tmp_path, near_ties=0):
+    """Run the CLI on the GPU and the same host pipeline with the C oracle as the kernel."""
+    from oracle import oracle_c
+    from ballermixplus_b200 import windows
+    from ballermixplus_b200.problem import build_problem
+    from ballermixplus_b200.scan import HEADER, format_rows
+    lines = run_cli(argv, str(tmp_path / 'out.txt'))
+    opt, data, neutral, grid, sel = util.host_objects(argv)
+    prob, order = build_problem(data, neutral, sel, grid)
+    with util.quiet():
+        plan = windows.make_plan(data, fixSize=opt.size, r=opt.w, s=opt.step, phys=opt.phys, noCenter=opt.noCenter)
+    t, lo, hi, gap = plan.arrays()
+    T, iA, ixa, ns, _ = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t, lo, hi)
+    ix = np.where(ixa >= 0, ixa // prob.n_a, -1)
+    ia = np.where(ixa >= 0, ixa % prob.n_a, -1)
+    ref_path = str(tmp_path / 'oracle.txt')
+    with open(ref_path, 'w') as fh:
+        fh.write(HEADER)
+        fh.writelines(format_rows(plan, order, T, iA, ix, ia, ns))
+    return lines, util.compare_scan(lines, ref_path, rtol=1e-9, max_near_ties=near_ties)
+
+
+D = 'data/'
+
+
+def test_flags_the_reference_crashes_on(tmp_path):
+    """--rangeA, --findPos and --minCount with --noFreq have no reference output:
+    checked against the oracle driven by the same host objects, and --rangeA against --listA."""
+    ex1 = ['-i', D + 'Example1_fullSweep_200kya_DAF.txt', '--spect', D + 'HC_CEU_Neut_DAF_spect_for_B2.txt']
+    a, _ = _cli_vs_oracle(ex1 + ['--rangeA', '500,4500,1000', '-s', '40'], tmp_path)
+    b, _ = _cli_vs_oracle(ex1 + ['--listA', '500,1500,2500,3500,4500', '-s', '40'], tmp_path)
+    assert a == b and len(a) == 20
+    # the --findPos x grid holds both x and 1-x, whose folded tables are mathematically identical:
+    # every row is an exact tie between the two, resolved by rounding (hence near_ties = all rows)
+    lines, (n, same, worst, ties) = _cli_vs_oracle(ex1 + ['--findPos', '-s', '60'], tmp_path, near_ties=14)
+    assert n == 14 and all(float(l.split('\t')[3]) < 1.0 for l in lines[1:])
+    b1 = ['-i', D + 'Example2_balancing_10MYA_DAF.txt', '--spect', D + 'HC_CEU_Neut_config_for_B1.txt', '--noFreq']
+    _cli_vs_oracle(b1 + ['--minCount', '2', '-s', '70', '--listA', '100,1000,1e4'], tmp_path, near_ties=1)
+
+
+def test_calcballer_drop_in_one_centre_at_a_time():
+    """The reference's per-centre seam (v1:436): same signature, same 5-element list."""
+    from oracle import oracle_np
+    from ballermixplus_b200 import calcBaller
+    argv, _ = CASES['ex1_B2_w15_s7p5']
+    opt, data, neutral, grid, sel = util.host_objects(argv)
+    A, x, a = grid.scan_order()
+    for i in (0, 233, 756):
+        lo, hi = max(0, i - 15), min(data.numSites - 1, i + 16)
+        got = calcBaller(np.arange(lo, hi + 1), data.genPos[i], data, neutral, sel, grid)
+        want = oracle_np.calc_baller(lo, hi, data.genPos[i], data.genPos, neutral.probs, neutral.logProbs,
+                                     neutral.propSizes, {k: sel.get(*k) for k in sel.classProbs}, A, x, a)
+        assert got[1:] == want[1:] and type(got[2]) is type(want[2]) and type(got[3]) is type(want[3])
+        assert abs(got[0] - want[0]) <= 1e-9 * max(1., abs(want[0]))
+    assert calcBaller(np.arange(0), data.genPos[5], data, neutral, sel, grid) == [0., 0., 0., 0., 0.]
