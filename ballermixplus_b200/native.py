@@ -173,7 +173,7 @@ class Scanner:
         v, c = (C.c_uint64 * 6)(), C.c_uint64(0)
         _check(lib().blmx_last_counters6(self._h, C.byref(v), C.byref(c)))
         return {'pairs': v[0], 'single': v[1], 'far_updates': v[2], 'far_terms': v[3], 'far_sites': v[4],
-                'launches': c.value}
+                'range_violations': v[5], 'launches': c.value}
 
     def kernel_ms(self):
         """(summed scan-kernel ms, launches) of the most recent scan; needs option timing=1."""

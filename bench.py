@@ -337,7 +337,7 @@ def cuda_arm(opt, rank, world, local_rank):
             kms, kn = scanners[c].kernel_ms()
             k_ms += kms; k_n += kn
             for key, v in scanners[c].counters_all().items():
-                tot[key] += v
+                tot[key] = tot.get(key, 0) + v
         return tot, k_ms, k_n
 
     sync_all()

@@ -141,7 +141,8 @@ int blmx_last_counters(blmx_handle *h, uint64_t *site_pairs, uint64_t *single_pa
                        uint64_t *launches);
 /* All work counters: [0] site_pairs, [1] single_pairs, [2] far-field moment updates (one
  * DMUL + one DADD each), [3] far-field polynomial terms summed over class visits (one DFMA
- * per term and grid point), [4] site pairs that entered through the far field, [5] reserved. */
+ * per term and grid point), [4] site pairs that entered through the far field, [5] index-range violations
+ * (always 0; counted only by the -DBLMX_CHECKED build the tests run). */
 int blmx_last_counters6(blmx_handle *h, uint64_t *six, uint64_t *launches);
 
 /*

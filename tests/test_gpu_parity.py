@@ -267,3 +267,45 @@ def test_calcballer_drop_in_one_centre_at_a_time():
         assert got[1:] == want[1:] and type(got[2]) is type(want[2]) and type(got[3]) is type(want[3])
         assert abs(got[0] - want[0]) <= 1e-9 * max(1., abs(want[0]))
     assert calcBaller(np.arange(0), data.genPos[5], data, neutral, sel, grid) == [0., 0., 0., 0., 0.]
+
+
+def test_range_checked_build_sees_no_violation():
+    """The -DBLMX_CHECKED build counts every out-of-range index the scan kernel would form
+    (compute-sanitizer is closed on the GPU pool): ragged windows, shuffled input, tiny and
+    huge grids, both kernel modes -- the counter must stay 0 and results must not change."""
+    import subprocess
+    import sys
+    lib = os.path.join(util.ROOT, 'ballermixplus_b200', 'libblmx_checked.so')
+    assert os.path.exists(lib), 'run __graft_entry__.build() first'
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import util
+from ballermixplus_b200.native import Scanner, ScanProblem
+from ballermixplus_b200.problem import build_problem
+rng = np.random.default_rng(17)
+bad = 0
+for name in ('Example2_B2', 'Example1_B1', 'ex1_B2_fixgrid', 'synth_mixed_n_B2_s20', 'synth_n200_B2_s700'):
+    argv, _ = util.scan_cases()[name]
+    opt, data, neutral, grid, sel = util.host_objects(argv)
+    prob, order = build_problem(data, neutral, sel, grid)
+    n = data.numSites
+    perm = rng.permutation(n)
+    shuffled = ScanProblem(prob.genpos[perm], prob.cls[perm], prob.G, prob.SP, prob.A, prob.n_x, prob.n_a)
+    c = rng.integers(0, n, size=150)
+    t = data.genPos[c] + np.where(rng.random(150) < 0.2, 1e-7, 0.0)
+    lo = c - rng.integers(-20, 900, size=150)
+    hi = c + rng.integers(-20, 900, size=150)
+    for p in (prob, shuffled):
+        res = []
+        for ff in (0, 1):
+            with Scanner(device=0, farfield=ff, batch=37).load(p) as sc:
+                res.append(sc.scan(t, lo, hi))
+                bad += sc.counters_all()['range_violations']
+        assert np.allclose(res[0][0], res[1][0], rtol=1e-10, atol=1e-10)
+print('VIOLATIONS', bad)
+''' % (util.ROOT, os.path.join(util.ROOT, 'tests'))
+    env = dict(os.environ, BLMX_LIB=lib)
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'VIOLATIONS 0' in out.stdout, out.stdout[-500:]
