@@ -135,7 +135,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200', '-i', str(self.device)],
+                                          '-lms', '100', '-i', str(self.device)],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None

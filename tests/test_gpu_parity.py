@@ -309,3 +309,38 @@ print('VIOLATIONS', bad)
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert 'VIOLATIONS 0' in out.stdout, out.stdout[-500:]
+
+
+def test_full_size_chromosome_properties():
+    """BASELINE.json's full size (chromosome 1 of the 10 M-site genome: 846 k sites, n = 200,
+    100 A x 510 grid, windows of up to 53 k sites): the two kernel modes agree on 96 centres, the
+    C oracle confirms two of them, and centres give the same row whatever batch they travel in."""
+    import bench
+    from oracle import oracle_c
+    from ballermixplus_b200.native import Scanner
+    sizes = bench.genome_sizes(10_000_000)
+    chrom = bench.make_chromosome(int(sizes[0]), seed=12345)
+    prob = bench.make_problem([chrom])[0]
+    n = len(prob.genpos)
+    assert n > 800_000
+    c = np.linspace(0, n - 1, 96).astype(np.int64)
+    t, lo, hi = prob.genpos[c], np.zeros(len(c), np.int64), np.full(len(c), n - 1, np.int64)
+    with Scanner(device=0, farfield=1).load(prob) as sc:
+        far = sc.scan(t, lo, hi)
+        cnt = sc.counters_all()
+        sc.set_option('batch', 7)
+        far_b = sc.scan(t, lo, hi)
+    with Scanner(device=0, farfield=0).load(prob) as sc:
+        direct = sc.scan(t, lo, hi)
+    assert cnt['far_sites'] > 0.7 * cnt['pairs']
+    for a, b in zip(far, far_b):
+        assert np.array_equal(a, b)
+    assert np.all(np.abs(far[0] - direct[0]) <= 1e-10 * np.maximum(np.abs(direct[0]), 1.))
+    for a, b in zip(far[1:], direct[1:]):
+        assert np.array_equal(a, b)
+    assert cnt['pairs'] > 96 * 100 * 10_000              # ~12.7 k sites per (centre, A) on average
+    pick = np.array([1, 48])
+    rT, rA, rxa, rn, _ = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t[pick], lo[pick], hi[pick])
+    assert np.array_equal(far[1][pick], rA) and np.array_equal(far[2][pick] * prob.n_a + far[3][pick], rxa)
+    assert np.array_equal(far[4][pick], rn)
+    assert np.all(np.abs(far[0][pick] - rT) <= 1e-9 * np.maximum(np.abs(rT), 1.))
