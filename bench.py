@@ -61,9 +61,8 @@ def make_chromosome(n_sites, seed, n=N_SAMPLE, spacing=SPACING):
     length = max(n_sites * spacing, n_sites + 2)
     pos = np.sort(rng.choice(length - 1, size=n_sites, replace=False)).astype(np.int64) + 1
     is_sub = rng.random(n_sites) < 0.7
-    kmax = int(os.environ.get('BLMX_BENCH_KMAX', n))       # experiment knob: fewer (k, n) classes
-    w = 1. / np.arange(1, kmax)
-    k = np.where(is_sub, n, rng.choice(np.arange(1, kmax), size=n_sites, p=w / w.sum())).astype(np.int64)
+    w = 1. / np.arange(1, n)
+    k = np.where(is_sub, n, rng.choice(np.arange(1, n), size=n_sites, p=w / w.sum())).astype(np.int64)
     return {'pos': pos, 'k': k, 'n': n}
 
 
