@@ -17,25 +17,35 @@ CASES = util.scan_cases()
 NEAR_TIES = {'Example2_B1': 12}      # two-class B1 tables: T of different (x, a) agree to ~1e-13
 
 
-def host_scan_with_oracle(argv):
+# the six full-length shipped goldens are evaluated on every third row here (the GPU suite does all rows)
+ROW_STRIDE = {'Example1_B1': 3, 'Example1_B2': 3, 'Example1_B2maf': 3, 'Example2_B1': 3, 'Example2_B2': 3,
+              'Example2_B2maf': 3}
+
+
+def host_scan_with_oracle(argv, stride=1):
     opt, data, neutral, grid, sel = util.host_objects(argv)
     prob, order = build_problem(data, neutral, sel, grid)
     with util.quiet():
         plan = windows.make_plan(data, fixSize=opt.size, r=opt.w, s=opt.step, phys=opt.phys,
                                  noCenter=opt.noCenter)
     t, lo, hi, gap = plan.arrays()
-    T, iA, ixa, ns, _ = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t, lo, hi)
+    rows = np.arange(0, len(t), stride)
+    T = np.zeros(len(t)); iA = np.full(len(t), -1, np.int32); ixa = iA.copy(); ns = np.zeros(len(t), np.int32)
+    T[rows], iA[rows], ixa[rows], ns[rows], _ = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A,
+                                                              t[rows], lo[rows], hi[rows])
     ix = np.where(ixa >= 0, ixa // prob.n_a, -1)
     ia = np.where(ixa >= 0, ixa % prob.n_a, -1)
-    return [HEADER] + format_rows(plan, order, T, iA, ix, ia, ns)
+    lines = format_rows(plan, order, T, iA, ix, ia, ns)
+    keep = set(rows.tolist())
+    return [HEADER] + [ln if j in keep else None for j, ln in enumerate(lines)]
 
 
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_host_pipeline_reproduces_golden(name):
     argv, gold = CASES[name]
-    lines = host_scan_with_oracle(argv)
+    lines = host_scan_with_oracle(argv, ROW_STRIDE.get(name, 1))
     n, same, worst, ties = util.compare_scan(lines, gold, rtol=1e-9, max_near_ties=NEAR_TIES.get(name, 0))
-    assert n == len(lines)
+    assert n == sum(ln is not None for ln in lines) and n >= 4
 
 
 @pytest.mark.parametrize('name', ['Example1_B2', 'Example1_B2maf', 'Example1_B1', 'ex2_B0_s5',
