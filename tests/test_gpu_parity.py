@@ -345,3 +345,14 @@ def test_full_size_chromosome_properties():
     assert np.array_equal(far[1][pick], rA) and np.array_equal(got_xa, rxa)
     assert np.array_equal(far[4][pick], rn)
     assert np.all(np.abs(far[0][pick] - rT) <= 1e-9 * np.maximum(np.abs(rT), 1.))
+
+
+def test_randomised_parity_campaign():
+    """20 s of tools/fuzz_parity.py: random tables (huge, underflowing, exact zeros), grids, windows,
+    sorted and shuffled inputs, all three kernel modes against the C oracle."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(util.ROOT, 'tools', 'fuzz_parity.py'), '--seconds', '20',
+                          '--seed', '7'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert 'DONE:' in out.stdout
