@@ -204,6 +204,29 @@ def run_cpu_oracle(problems, plans, sample, threads):
     return time.perf_counter() - t0, centres, pairs
 
 
+def run_numpy_oracle_one_centre(problems, plans):
+    """The vectorised numpy restatement (oracle/oracle_np.py, what the reference's numpy/scipy path
+    costs once its Python-list indexing overhead is removed), ONE interior centre, one thread."""
+    from oracle import oracle_np
+    c = int(np.argmax([len(p.genpos) for p in problems]))
+    p = problems[c]
+    t = plans[c][0]
+    tj = float(t[len(t) // 2])
+    reach = 18.420680743952367 / float(p.A.min()) * 1.001
+    lo = int(np.searchsorted(p.genpos, tj - reach, 'left'))
+    hi = int(np.searchsorted(p.genpos, tj + reach, 'right'))
+    g = p.genpos[lo:hi]
+    cls = p.cls[lo:hi]
+    probs = p.G[cls]
+    selmat = np.ascontiguousarray(p.SP[:, cls])
+    t0 = time.perf_counter()
+    oracle_np.calc_baller_fast(0, len(g) - 1, tj, g, probs, np.log(probs), np.ones_like(probs), selmat, p.A)
+    secs = time.perf_counter() - t0
+    n_grid = p.n_x * p.n_a * len(p.A)
+    return {'value': n_grid / secs, 'unit': 'centre*gridpoint/s', 'cores': 1, 'kind': 'port',
+            'sample': f'1 interior centre, {n_grid} grid points, numpy restatement (oracle/oracle_np.py), {secs:.1f} s'}
+
+
 # ---------------------------------------------------------------------------------- arms
 def reference_arm(opt, rank):
     """CPU arm: the oracle's C port of calcBaller on all host threads (the reference itself is a
@@ -487,6 +510,7 @@ def cuda_arm(opt, rank, world, local_rank):
                 'sample': f'{centres} centres spread evenly over the genome, all {n_grid} grid points each, '
                           f'literal calcBaller in C (oracle/oracle_c.c), OpenMP on {threads} threads, {secs:.1f} s',
                 'site_evals_per_s': cpairs * n_xa / secs}
+            line['cpu_baseline_numpy'] = run_numpy_oracle_one_centre(problems, plans)
         print(json.dumps(line), flush=True)
     for s in scanners.values():
         s.close()
