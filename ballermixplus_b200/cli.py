@@ -7,6 +7,7 @@ DESIGN.md "flags without a reference behaviour"): ``--rangeA``, ``--findPos`` an
 ``--minCount`` with ``--noFreq`` work here.
 """
 import argparse
+import os
 import sys
 from datetime import datetime
 
@@ -65,6 +66,8 @@ def build_parser():
 
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else list(argv)
+    if int(os.environ.get('RANK', '0')) != 0:          # torchrun: only rank 0 talks and writes
+        sys.stdout = open(os.devnull, 'w')
     parser = build_parser()
     if len(argv) == 0:
         parser.print_help()

@@ -88,13 +88,57 @@ def write_scan(outfile, plan, order, T, iA, ix, ia, ns):
         scores.writelines(format_rows(plan, order, T, iA, ix, ia, ns))
 
 
+def _world():
+    """(rank, world, local_rank) of a torchrun launch, (0, 1, 0) otherwise."""
+    return (int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')),
+            int(os.environ.get('LOCAL_RANK', '0')))
+
+
+def scan_rows_multi_gpu(dev, t, lo, hi, rank, world, local_rank):
+    """One process per GPU (torchrun): every rank scans a cost-balanced contiguous slice of the centres,
+    one gather brings the rows to rank 0 (sharding.py).  NCCL when every rank has its own GPU, else gloo
+    over host tensors (several ranks sharing one device, e.g. in tests).  Returns the five result
+    arrays on rank 0 and None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from . import sharding
+    from .native import device_count
+    own_gpu = device_count() >= world
+    started = not dist.is_initialized()
+    if started:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        dist.init_process_group('nccl' if own_gpu else 'gloo', rank=rank, world_size=world)
+    where = torch.device('cuda', local_rank) if own_gpu else torch.device('cpu')
+
+    def scan_fn(ts, los, his):
+        T, iA, ix, ia, ns = dev.run(ts, los, his)
+        return tuple(torch.from_numpy(np.ascontiguousarray(a)).to(where) for a in (T, iA, ix, ia, ns))
+
+    try:
+        got = sharding.scan_sharded(dev.problem.genpos, dev.problem.A, t, lo, hi, rank, world, scan_fn, dist, torch)
+        return None if got is None else tuple(a.cpu().numpy() for a in got)
+    finally:
+        if started:
+            dist.barrier()
+            dist.destroy_process_group()
+
+
 class Scan:
-    """Same constructor as the reference class (v1:613); runs the scan and writes ``outfile``."""
+    """Same constructor as the reference class (v1:613); runs the scan and writes ``outfile``.
+
+    Launched under ``torchrun --nproc-per-node N`` the centres are sharded over N GPUs and rank 0
+    writes the file (the other ranks write nothing)."""
 
     def __init__(self, InputData, NeutralSFS, NormalizedBetaBinom, Grids, outfile, fixSize=False,
                  r=0, s=1, phys=False, noCenter=False, device=0):
+        rank, world, local_rank = _world()
         plan = windows.make_plan(InputData, fixSize=fixSize, r=r, s=s, phys=phys, noCenter=noCenter)
-        print('writing output to %s' % (outfile))
+        if rank == 0:
+            print('writing output to %s' % (outfile))
+        if world > 1:
+            from .native import device_count
+            device = local_rank % max(1, device_count())
         dev = DeviceScan(InputData, NeutralSFS, NormalizedBetaBinom, Grids, device=device)
         try:
             t, lo, hi, gap = plan.arrays()
@@ -102,9 +146,16 @@ class Scan:
             T = np.zeros(len(plan)); iA = np.full(len(plan), -1, np.int32)
             ix = iA.copy(); ia = iA.copy(); ns = np.zeros(len(plan), np.int32)
             if len(live):
-                T[live], iA[live], ix[live], ia[live], ns[live] = dev.run(t[live], lo[live], hi[live])
-            self.results = (T, iA, ix, ia, ns)
-            write_scan(outfile, plan, dev.order, T, iA, ix, ia, ns)
+                if world > 1:
+                    got = scan_rows_multi_gpu(dev, t[live], lo[live], hi[live], rank, world, local_rank)
+                else:
+                    got = dev.run(t[live], lo[live], hi[live])
+                if got is not None:
+                    T[live], iA[live], ix[live], ia[live], ns[live] = got
+            self.results = (T, iA, ix, ia, ns) if rank == 0 else None
+            if rank == 0:
+                write_scan(outfile, plan, dev.order, T, iA, ix, ia, ns)
         finally:
             dev.close()
-        print(f'{datetime.now()}. Scan finished.')
+        if rank == 0:
+            print(f'{datetime.now()}. Scan finished.')

@@ -356,3 +356,20 @@ def test_randomised_parity_campaign():
                           '--seed', '7'], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert 'DONE:' in out.stdout
+
+
+def test_cli_under_torchrun_two_ranks(tmp_path):
+    """`torchrun --nproc-per-node 2 -m ballermixplus_b200 ...`: the centres are sharded over two ranks
+    (sharing the one GPU of the test box, so the gather runs over gloo), rank 0 writes the same file."""
+    import subprocess
+    import sys
+    argv, gold = CASES['ex1_B2_w20_s10']
+    out = str(tmp_path / 'out.txt')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', '29533', '-m', 'ballermixplus_b200'] + util.abs_paths(argv) + ['-o', out]
+    res = subprocess.run(cmd, cwd=util.ROOT, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    with open(out) as fh:
+        lines = fh.read().splitlines(keepends=True)
+    n, same, worst, ties = util.compare_scan(lines, gold)
+    assert n == len(lines)
