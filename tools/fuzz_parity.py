@@ -20,9 +20,13 @@ from oracle import oracle_c                                    # noqa: E402
 from ballermixplus_b200.native import Scanner, ScanProblem      # noqa: E402
 
 
-def random_problem(rng):
-    n_sites = int(rng.choice([1, 2, 5, 40, 300, 2000, 20000]))
-    C = int(rng.choice([1, 2, 3, 17, 60, 250]))
+def random_problem(rng, big=False):
+    if big:                      # long class runs: the far-field path does most of the work
+        n_sites = int(rng.choice([3000, 20000, 60000]))
+        C = int(rng.choice([1, 2, 5, 12]))
+    else:
+        n_sites = int(rng.choice([1, 2, 5, 40, 300, 2000, 20000]))
+        C = int(rng.choice([1, 2, 3, 17, 60, 250]))
     n_x = int(rng.choice([1, 2, 5, 10]))
     n_a = int(rng.choice([1, 3, 7, 51, 70]))
     n_A = int(rng.choice([1, 2, 9, 40]))
@@ -47,7 +51,7 @@ def random_problem(rng):
     A = 10.0 ** rng.uniform(0, 9, n_A)
     A *= 18.42 / (A.min() * span) * 10.0 ** rng.uniform(-2, 2)                     # windows from tiny to all sites
     prob = ScanProblem(g, cls, G, SP, A, n_x, n_a)
-    m = int(rng.choice([1, 7, 60]))
+    m = int(rng.choice([1, 7, 60])) if not big else int(rng.choice([4, 16]))
     c = rng.integers(0, n_sites, m)
     t = g[c] + np.where(rng.random(m) < 0.3, span * 10.0 ** rng.uniform(-9, -3, m), 0.0)
     lo = c - rng.integers(-3, max(2, n_sites), m)
@@ -59,13 +63,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--seconds', type=float, default=300)
     ap.add_argument('--seed', type=int, default=1)
+    ap.add_argument('--big', action='store_true', help='large problems with long class runs (far field)')
     opt = ap.parse_args()
     rng = np.random.default_rng(opt.seed)
     t_end = time.time() + opt.seconds
     n = 0
     worst = 0.0
     while time.time() < t_end:
-        prob, t, lo, hi = random_problem(rng)
+        prob, t, lo, hi = random_problem(rng, opt.big)
         rT, rA, rxa, rn, rpairs = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t, lo, hi)
         for mode in ((1, 0), (4, 0), (4, 1)):
             with Scanner(device=0, group=mode[0], farfield=mode[1], batch=int(rng.choice([1, 5, 4096]))).load(prob) as sc:
@@ -88,7 +93,7 @@ def main():
             if rel.size:
                 worst = max(worst, float(rel.max()))
         n += 1
-        if n % 25 == 0:
+        if n % (5 if opt.big else 25) == 0:
             print(f'{n} problems ok, worst |dT|/max(|T|,1) = {worst:.2e}', flush=True)
     print(f'DONE: {n} random problems x 3 kernel modes agree with the oracle; worst |dT|/max(|T|,1) = {worst:.2e}')
 
