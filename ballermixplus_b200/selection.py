@@ -40,6 +40,11 @@ def stat_name(nofreq, MAF, nosub):
 
 
 class NormalizedBetaBinom:
+    """Built per (k, n) class with ONE broadcast scipy call per sample size and side of the fold
+    (x and 1-x): ``betabinom.pmf(j, n, a, b)`` over j = 0..n and the whole (x, a) grid.  scipy evaluates
+    the pmf elementwise, so every entry has the bits of the reference's per-(x, a) frozen-distribution
+    calls (tests/test_reference_objects.py compares all tables with the reference's, bit for bit;
+    ``_slow_row`` keeps the call-for-call form for tests/test_host_pipeline.py)."""
 
     @staticmethod
     def _get_b(x, a):
@@ -56,22 +61,54 @@ class NormalizedBetaBinom:
         if self.stat == 'B1':
             for n in sizes:
                 assert set(self.class_k[members[n]].tolist()) == {0, 1}
-        for x in Grids.x:
-            for a in Grids.abeta:
-                if (x, a) in self.classProbs:
-                    continue
-                row = np.zeros(len(self.class_k))
-                for n in sizes:
-                    k = self.class_k[members[n]]
-                    folded = 0.5 * (self._raw(k, n, x, a) + self._raw(k, n, 1. - x, a))
-                    row[members[n]] = folded / self._norm_base(n, x, a)
-                self.classProbs[(x, a)] = row
+        xs, alphas = list(Grids.x), list(Grids.abeta)
+        rows = {(x, a): np.zeros(len(self.class_k)) for x in xs for a in alphas}
+        avec = np.array([float(a) for a in alphas])
+        for n in sizes:
+            j = np.arange(n + 1)
+            # pmf[side][ix][ia][j]; b = a/x - a in Python arithmetic exactly as v1:316 forms it
+            pmf = []
+            for side in (lambda x: x, lambda x: 1. - x):
+                bmat = np.array([[self._get_b(side(x), a) for a in alphas] for x in xs], dtype=np.float64)
+                pmf.append(betabinom.pmf(j[None, None, :], n, avec[None, :, None], bmat[:, :, None]))
+            k = self.class_k[members[n]]
+            excl = self._excluded(n)
+            for ix, x in enumerate(xs):
+                for ia, a in enumerate(alphas):
+                    px, pc = pmf[0][ix, ia], pmf[1][ix, ia]
+                    folded = 0.5 * (self._raw_from(px, k, n) + self._raw_from(pc, k, n))
+                    base = 1. - np.sum(0.5 * (px[excl] + pc[excl]))
+                    rows[(x, a)][members[n]] = folded / base
+        self.classProbs = rows
 
     def get(self, x, a):
         """Per-site normalised selection probabilities (reference API, v1:362)."""
         return self.classProbs[(x, a)][self.cls]
 
     # -- pieces -----------------------------------------------------------------
+    def _raw_from(self, p, k, n):
+        """Unfolded probabilities of the classes k from the pmf p[0..n] (v1:375-396)."""
+        s = self.stat
+        if s == 'B1':
+            return np.where(k == 0, p[n], (1. - p[n] - p[n]))
+        if s in ('B2', 'B0'):
+            return p[k]
+        probs = p[k] + p[n - k]
+        if n % 2 == 0:
+            probs = np.where(k == int(n / 2), probs / 2, probs)
+        return probs
+
+    def _slow_row(self, x, a):
+        """The same row built call for call as the reference does (v1:337-355); tests only."""
+        sizes = sorted(set(self.class_n.tolist()))
+        row = np.zeros(len(self.class_k))
+        for n in sizes:
+            idx = np.flatnonzero(self.class_n == n)
+            k = self.class_k[idx]
+            folded = 0.5 * (self._raw(k, n, x, a) + self._raw(k, n, 1. - x, a))
+            row[idx] = folded / self._norm_base(n, x, a)
+        return row
+
     def _pmf(self, j, n, x, a):
         key = (n, x, a)
         d = self._dist.get(key)

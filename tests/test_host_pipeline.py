@@ -142,3 +142,14 @@ def test_window_planners_match_oracle_rows():
             else:
                 assert (plan.t[j], plan.lo[j], plan.hi[j], plan.f0[j], plan.f1[j]) == \
                        (row['t'], row['lo'], row['hi'], row['f0'], row['f1'])
+
+
+@pytest.mark.parametrize('name', ['Example1_B2', 'Example2_B2maf', 'Example1_B1', 'ex2_B0_s5',
+                                  'Example2_B0maf_1kb-2site', 'synth_mixed_n_B2_s20', 'ex2_B2maf_findBal_s60'])
+def test_broadcast_tables_equal_call_for_call_tables(name):
+    """The one-scipy-call-per-sample-size table build against the reference's call-for-call form."""
+    argv, _ = CASES[name]
+    opt, data, neutral, grid, sel = util.host_objects(argv)
+    for x in grid.x[::2]:
+        for a in grid.abeta[::4] + grid.abeta[-3:]:
+            assert np.array_equal(sel.classProbs[(x, a)], sel._slow_row(x, a)), (x, a)
