@@ -78,12 +78,25 @@ def plan_alpha(data, s):
     return plan
 
 
+def _sorted(a):
+    return len(a) < 2 or bool(np.all(a[1:] >= a[:-1]))
+
+
 def plan_site_based(data, r, s):
     """-w r (v1:580-594): r sites to the left, r+1 to the right, centre index int(i)."""
     if not s > 0:
         raise ValueError('-s/--step must be positive')
     N = data.numSites
     plan = ScanPlan()
+    if float(s).is_integer() and float(r).is_integer():
+        # whole-number steps (the usual case; argparse hands -s over as a float): same ranges, as arrays
+        c = np.arange(0, N, int(s), dtype=np.int64)
+        plan.t = data.genPos[c]
+        plan.lo = np.maximum(0, c - int(r))
+        plan.hi = np.minimum(N - 1, c + int(r) + 1)
+        plan.gap = np.zeros(len(c), bool)
+        plan.set_sites(data, c)
+        return plan
     i = 0
     centres = []
     while i < N:
@@ -104,6 +117,18 @@ def plan_fixsize_site_center(data, w, s):
     N = data.numSites
     pos = data.position
     plan = ScanPlan()
+    if N and _sorted(pos):
+        # sorted positions: the reference's two monotone pointers are two binary searches
+        idx = np.arange(0, N, step, dtype=np.int64)
+        ts = pos[idx]
+        start = np.maximum(0, ts - w / 2)
+        end = np.minimum(ts + w / 2, pos[-1])
+        plan.t = data.genPos[idx]
+        plan.lo = np.searchsorted(pos, start, 'left').astype(np.int64)
+        plan.hi = np.minimum(np.searchsorted(pos, end, 'left'), N - 1).astype(np.int64)
+        plan.gap = np.zeros(len(idx), bool)
+        plan.set_sites(data, idx)
+        return plan
     si = ei = 0
     last = pos[-1] if N else 0
     for i in range(0, N, step):

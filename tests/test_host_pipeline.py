@@ -129,7 +129,8 @@ def test_window_planners_match_oracle_rows():
     rng = np.random.default_rng(7)
     pos = np.sort(rng.choice(np.arange(5, 30000), 300, replace=False))
     data = InputData.from_arrays(pos, pos * 1e-6, np.ones(300, int), np.full(300, 10))
-    for kw in (dict(), dict(s=7.0), dict(r=12, s=1), dict(r=9, s=2.5), dict(fixSize=True, r=900, s=3.0),
+    for kw in (dict(), dict(s=7.0), dict(r=12, s=1), dict(r=9, s=2.5), dict(r=400, s=4.0), dict(r=3, s=1.0),
+               dict(fixSize=True, r=900, s=3.0), dict(fixSize=True, r=1, s=1.0), dict(fixSize=True, r=10 ** 6, s=50.0),
                dict(fixSize=True, r=2000, s=500.0, noCenter=True), dict(fixSize=True, r=300, s=150.0, noCenter=True)):
         with util.quiet():
             plan = windows.make_plan(data, phys=True, **kw)
