@@ -373,3 +373,30 @@ def test_cli_under_torchrun_two_ranks(tmp_path):
         lines = fh.read().splitlines(keepends=True)
     n, same, worst, ties = util.compare_scan(lines, gold)
     assert n == len(lines)
+
+
+def test_oneshot_and_timing_entry_points():
+    """blmx_scan_oneshot (create + load + scan + destroy) and the per-launch kernel timing."""
+    import ctypes as C
+    from ballermixplus_b200 import native
+    data, prob, order = _problem('ex1_B2_fixgrid')
+    c = np.arange(0, data.numSites, 7)
+    t = np.ascontiguousarray(data.genPos[c])
+    lo = np.zeros(len(c), np.int64)
+    hi = np.full(len(c), data.numSites - 1, np.int64)
+    with native.Scanner(device=0).load(prob) as sc:
+        sc.set_option('timing', 1)
+        want = sc.scan(t, lo, hi)
+        ms, n_launch = sc.kernel_ms()
+        assert n_launch == 1 and 0 < ms < 1000
+    T = np.zeros(len(c)); iA, ix, ia, ns = (np.zeros(len(c), np.int32) for _ in range(4))
+    res = native.Result(*(a.ctypes.data_as(C.c_void_p) for a in (T, iA, ix, ia, ns)))
+    st = prob.as_struct()
+    rc = native.lib().blmx_scan_oneshot(0, C.byref(st), len(c), t.ctypes.data_as(C.c_void_p),
+                                        lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), C.byref(res))
+    assert rc == 0, native.lib().blmx_last_error()
+    for a, b in zip((T, iA, ix, ia, ns), want):
+        assert np.array_equal(a, b)
+    # errors come back as codes with a message, never as exceptions or exits
+    rc = native.lib().blmx_scan_oneshot(0, C.byref(st), len(c), None, None, None, C.byref(res))
+    assert rc == -1 and b'null' in native.lib().blmx_last_error()
