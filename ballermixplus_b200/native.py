@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get('BLMX_LIB') or os.path.join(_HERE, 'libblmx.so')   # B
 ABI_SYMBOLS = (
     'blmx_abi_version', 'blmx_last_error', 'blmx_device_count', 'blmx_create', 'blmx_destroy',
     'blmx_load', 'blmx_scan', 'blmx_scan_device', 'blmx_scan_oneshot', 'blmx_set_option',
-    'blmx_last_counters', 'blmx_last_counters6', 'blmx_last_kernel_ms', 'blmx_measure_fp64_peak',
+    'blmx_last_counters', 'blmx_last_counters6', 'blmx_last_counters8', 'blmx_problem_info',
+    'blmx_last_kernel_ms', 'blmx_measure_fp64_peak',
 )
 
 
@@ -60,6 +61,9 @@ def lib():
         L.blmx_last_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_uint64)]
         L.blmx_last_counters6.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 6), C.POINTER(C.c_uint64)]
+        L.blmx_last_counters8.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 8), C.POINTER(C.c_uint64)]
+        L.blmx_problem_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int64)]
         L.blmx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.blmx_measure_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double),
                                              C.POINTER(C.c_double)]
@@ -162,18 +166,18 @@ class Scanner:
         _check(lib().blmx_last_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, c.value
 
-    def counters_full(self):
-        """(site pairs, of which evaluated singly, launches) of the most recent scan."""
-        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
-        _check(lib().blmx_last_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
-
     def counters_all(self):
-        """dict of the work counters of the most recent scan (see blmx_last_counters6)."""
-        v, c = (C.c_uint64 * 6)(), C.c_uint64(0)
-        _check(lib().blmx_last_counters6(self._h, C.byref(v), C.byref(c)))
-        return {'pairs': v[0], 'single': v[1], 'far_updates': v[2], 'far_terms': v[3], 'far_sites': v[4],
-                'range_violations': v[5], 'launches': c.value}
+        """dict of the work counters of the most recent scan (see blmx_last_counters8)."""
+        v, c = (C.c_uint64 * 8)(), C.c_uint64(0)
+        _check(lib().blmx_last_counters8(self._h, C.byref(v), C.byref(c)))
+        return {'pairs': v[0], 'single': v[1], 'far_blocks': v[2], 'far_terms': v[3], 'far_sites': v[4],
+                'range_violations': v[5], 'edge_sites': v[6], 'quads': v[7], 'launches': c.value}
+
+    def problem_info(self):
+        """Far-field layout of the loaded problem: whole blocks, sites per block, bytes of moments in HBM."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _check(lib().blmx_problem_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {'far_blocks': a.value, 'far_block_sites': b.value, 'moment_bytes': c.value}
 
     def kernel_ms(self):
         """(summed scan-kernel ms, launches) of the most recent scan; needs option timing=1."""

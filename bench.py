@@ -39,19 +39,25 @@ RANGE_A = '1000,10900,100'
 BASE_STRIDE = 1024
 FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12        # 37.2: 148 SM x 64 DFMA/clk x 1.965 GHz
 # algorithmic FP64 flops (FMA = 2, MUL/ADD = 1; libdevice exp = 31, log = 47)
-FLOP_SINGLE = 3.0          # 1 + alpha*D (FMA) and the running product (MUL), per site and grid point
-FLOP_GROUPED = 2.25        # four sites: 4 FMA (quartic in D) + 1 MUL
-FLOP_EXP = 34.0            # alpha = exp(-A*|g - t|): once per (centre, A, site)
+FLOP_SINGLE = 3.0          # (1-alpha) + alpha*R (FMA) and the running product (MUL), per site and grid point
+FLOP_GROUPED = 2.25        # four sites: 4 FMA (quartic in R) + 1 MUL
+FLOP_EXP = 34.0            # alpha = exp(-A*|g - t|): once per (centre, A, site) evaluated site by site
+FLOP_QUAD_COEF = 23.0 / 4  # f0..f4 of a quartic from its four alphas (one lane), per grouped site
 FLOP_LOG = 47.0 + 3.0      # one log + exponent fold-in per (centre, A, grid point)
-FLOP_MOMENT = 2.0          # far field: alpha^m (MUL) added to S_m (ADD), per site and moment
+FLOP_BLOCK = 32 * (FLOP_EXP + 2.0)   # far field: one exp + one FMA on each of the 32 moment lanes, per block visit
+FLOP_EDGE = 9.0            # far field: five moments of a block-remainder site (besides its exp)
 FLOP_POLY = 2.0            # far field: one Horner FMA per polynomial term and grid point
 
 
 def algorithmic_flops(cnt, n_xa, n_items):
-    """FP64 flops the formulation needs for the work the kernel's own counters report."""
-    grouped = cnt['pairs'] - cnt['single'] - cnt['far_sites']
-    return (n_xa * (FLOP_SINGLE * cnt['single'] + FLOP_GROUPED * grouped) + FLOP_EXP * cnt['pairs']
-            + FLOP_MOMENT * cnt['far_updates'] + FLOP_POLY * n_xa * cnt['far_terms'] + FLOP_LOG * n_xa * n_items)
+    """FP64 flops the formulation needs for the work the kernel's own counters report:
+    sites evaluated per grid point (singly or four at a time), one exp per site that is looked at
+    individually, the far-field block visits / remainder sites / polynomial terms, one log per grid point."""
+    direct = cnt['pairs'] - cnt['far_sites']
+    grouped = direct - cnt['single']
+    return (n_xa * (FLOP_SINGLE * cnt['single'] + FLOP_GROUPED * grouped) + FLOP_QUAD_COEF * grouped
+            + FLOP_EXP * (direct + cnt['edge_sites']) + FLOP_EDGE * cnt['edge_sites']
+            + FLOP_BLOCK * cnt['far_blocks'] + FLOP_POLY * n_xa * cnt['far_terms'] + FLOP_LOG * n_xa * n_items)
 
 
 # ------------------------------------------------------------------------ synthetic data
@@ -353,7 +359,8 @@ def cuda_arm(opt, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     def collect():
         """Per-launch kernel events and work counters of the LAST step, summed over this rank's scanners."""
-        tot = {'pairs': 0, 'single': 0, 'far_updates': 0, 'far_terms': 0, 'far_sites': 0, 'launches': 0}
+        tot = {'pairs': 0, 'single': 0, 'far_blocks': 0, 'far_terms': 0, 'far_sites': 0, 'edge_sites': 0,
+               'quads': 0, 'launches': 0}
         k_ms, k_n = 0.0, 0
         for c, _ in mine:
             kms, kn = scanners[c].kernel_ms()

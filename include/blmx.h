@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BLMX_ABI_VERSION 1
+#define BLMX_ABI_VERSION 2
 
 typedef enum {
     BLMX_OK = 0,
@@ -120,11 +120,13 @@ int blmx_scan_oneshot(int device, const blmx_problem *p, int64_t n_centres, cons
 
 /*
  * Options (before or after load):
- *   "group"      1 = one FMA+MUL per site-evaluation; 4 = far sites are folded four
- *                at a time into a quartic in D (default)
- *   "farfield"   1 (default) = sites of a class with alpha*max|D| <= theta contribute through
- *                power sums of alpha (series of log(1 + alpha D), truncation < 2^-70 per site;
- *                needs group 4); 0 = every site is evaluated per grid point
+ *   "group"      1 = one FMA+MUL per site-evaluation; 4 = sites are folded four at a time into a
+ *                quartic in R = SP/G with non-negative coefficients (default)
+ *   "farfield"   1 (default) = sites of a class with alpha*max|D| <= 1/4 (D = SP/G - 1) contribute
+ *                through power sums of alpha (series of log(1 + alpha D), truncation < 2^-70 per
+ *                site), taken from per-block moments that blmx_load precomputes (the value at the
+ *                time of blmx_load decides whether they are built); 0 = every site is evaluated
+ *                per grid point
  *   "batch"      centres per kernel launch (scratch = batch * n_A * 16 bytes)
  *   "timing"     1 = record CUDA events around every scan kernel (see blmx_last_kernel_ms)
  */
@@ -139,11 +141,18 @@ int blmx_set_option(blmx_handle *h, const char *name, int64_t value);
  */
 int blmx_last_counters(blmx_handle *h, uint64_t *site_pairs, uint64_t *single_pairs,
                        uint64_t *launches);
-/* All work counters: [0] site_pairs, [1] single_pairs, [2] far-field moment updates (one
- * DMUL + one DADD each), [3] far-field polynomial terms summed over class visits (one DFMA
- * per term and grid point), [4] site pairs that entered through the far field, [5] index-range violations
- * (always 0; counted only by the -DBLMX_CHECKED build the tests run). */
+/* All work counters: [0] site_pairs, [1] single_pairs, [2] far-field block visits (one exp and
+ * one DFMA on each of 32 lanes), [3] far-field polynomial terms summed over class visits (one DFMA
+ * per term and grid point), [4] site pairs that entered through the far field, [5] index-range
+ * violations (always 0; counted only by the -DBLMX_CHECKED build the tests run), [6] of [4], the
+ * sites of block remainders summed one by one, [7] quartics evaluated (each covers up to four
+ * sites on every grid point). */
 int blmx_last_counters6(blmx_handle *h, uint64_t *six, uint64_t *launches);
+int blmx_last_counters8(blmx_handle *h, uint64_t *eight, uint64_t *launches);
+
+/* Far-field layout of the loaded problem: whole blocks, sites per block, bytes of block moments
+ * resident on the device (0 blocks: every site is evaluated directly). */
+int blmx_problem_info(blmx_handle *h, int64_t *far_blocks, int64_t *far_block_sites, int64_t *moment_bytes);
 
 /*
  * With option "timing" = 1 the library records a CUDA event pair around every scan-kernel

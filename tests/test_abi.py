@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(native.ABI_SYMBOLS) == names
-    assert L.blmx_abi_version() == 1
+    assert L.blmx_abi_version() == 2
 
 
 def test_product_does_not_import_the_oracle():

@@ -200,7 +200,7 @@ def test_synthetic_n200_against_oracle_sample():
     with Scanner(device=0, group=4, farfield=1).load(prob) as sc:
         rf = sc.scan(ta, loa, hia)
         far = sc.counters_all()
-    assert far['far_sites'] > 0.5 * far['pairs'] and far['far_terms'] > 0      # the far field was actually used
+    assert far['far_sites'] > 0.4 * far['pairs'] and far['far_terms'] > 0      # the far field was actually used
     assert np.allclose(r4[0], rf[0], rtol=1e-11, atol=1e-11)
     for a, b in zip(r4[1:], rf[1:]):
         assert np.array_equal(a, b)
@@ -332,7 +332,7 @@ def test_full_size_chromosome_properties():
         far_b = sc.scan(t, lo, hi)
     with Scanner(device=0, farfield=0).load(prob) as sc:
         direct = sc.scan(t, lo, hi)
-    assert cnt['far_sites'] > 0.7 * cnt['pairs']
+    assert cnt['far_sites'] > 0.6 * cnt['pairs']
     for a, b in zip(far, far_b):
         assert np.array_equal(a, b)
     assert np.all(np.abs(far[0] - direct[0]) <= 1e-10 * np.maximum(np.abs(direct[0]), 1.))
