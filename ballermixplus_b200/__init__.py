@@ -10,8 +10,8 @@ from .helpers import getConfig, getSpect
 from .inputs import InputData
 from .neutral import NeutralSFS
 from .selection import NormalizedBetaBinom
-from .scan import DeviceScan, Scan, calcBaller
+from .scan import DeviceScan, Scan, calcBaller, clear_cache
 from .cli import main
 
 __all__ = ['Grids', 'InputData', 'NeutralSFS', 'NormalizedBetaBinom', 'DeviceScan', 'Scan',
-           'calcBaller', 'getSpect', 'getConfig', 'main']
+           'calcBaller', 'clear_cache', 'getSpect', 'getConfig', 'main']

@@ -32,6 +32,22 @@ class DeviceScan:
         """-> (T float64[n], iA, ix, ia, nsites int32[n]); indices into the visiting order."""
         return self.scanner.scan(t, lo, hi)
 
+    def run_device(self, t, lo, hi, torch, device):
+        """Same scan with the centres uploaded once and the results LEFT ON THE DEVICE as torch tensors
+        (T float64, iA, ix, ia, nsites int32), asynchronous on torch's current stream: the multi-GPU path
+        hands them to the NCCL gather without a host round trip."""
+        n = len(t)
+        d_t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64)).to(device)
+        d_lo = torch.from_numpy(np.ascontiguousarray(lo, dtype=np.int64)).to(device)
+        d_hi = torch.from_numpy(np.ascontiguousarray(hi, dtype=np.int64)).to(device)
+        T = torch.zeros(n, dtype=torch.float64, device=device)
+        idx = [torch.full((n,), -1, dtype=torch.int32, device=device) for _ in range(4)]
+        idx[3].zero_()
+        self.scanner.scan_device(n, d_t.data_ptr(), d_lo.data_ptr(), d_hi.data_ptr(), T.data_ptr(),
+                                 *[x.data_ptr() for x in idx], stream=torch.cuda.current_stream(device).cuda_stream)
+        self._keep = (d_t, d_lo, d_hi)              # inputs stay alive until the stream has consumed them
+        return (T, *idx)
+
     def decode(self, T, iA, ix, ia, ns):
         return self.order.decode(T, iA, ix, ia, ns)
 
@@ -39,20 +55,33 @@ class DeviceScan:
         self.scanner.close()
 
 
-_cache = {}
+_cache = {}       # 'objs': the four host objects of the resident problem (strong references), 'dev': its DeviceScan
+
+
+def clear_cache():
+    """Release the GPU-resident problem that ``calcBaller`` keeps between calls."""
+    dev = _cache.pop('dev', None)
+    _cache.clear()
+    if dev is not None:
+        dev.close()
 
 
 def calcBaller(window_indice, testSite, InputData, NeutralSFS, NormalizedBetaBinom, Grids):
     """Drop-in for the reference function (v1:436): one centre, same 5-element result.
 
     ``window_indice`` must be a contiguous ascending index range, which is all the
-    reference's callers ever pass (v1:538,572,589,606).
+    reference's callers ever pass (v1:538,572,589,606).  The problem built from the four
+    objects stays on the GPU for the next call with the SAME objects (compared by identity,
+    and held here so that their ids cannot be recycled); mutating them in place between
+    calls is not detected -- call ``clear_cache()`` after doing so, and to free the device memory.
     """
-    key = (id(InputData), id(NeutralSFS), id(NormalizedBetaBinom), id(Grids))
-    dev = _cache.get(key)
-    if dev is None:
-        _cache.clear()
-        dev = _cache[key] = DeviceScan(InputData, NeutralSFS, NormalizedBetaBinom, Grids)
+    objs = (InputData, NeutralSFS, NormalizedBetaBinom, Grids)
+    held = _cache.get('objs')
+    if held is None or any(a is not b for a, b in zip(held, objs)):
+        clear_cache()
+        _cache['dev'] = DeviceScan(*objs)
+        _cache['objs'] = objs
+    dev = _cache['dev']
     w = np.asarray(window_indice)
     if len(w) == 0:
         return [0., 0., 0., 0., 0.]
@@ -94,33 +123,56 @@ def _world():
             int(os.environ.get('LOCAL_RANK', '0')))
 
 
+def _local_world():
+    """Ranks of this launch that run on THIS node (torchrun exports LOCAL_WORLD_SIZE)."""
+    return int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')))
+
+
+def ranks_own_a_gpu():
+    """True when every rank on this node can have its own CUDA device."""
+    from .native import device_count
+    return device_count() >= _local_world()
+
+
 def scan_rows_multi_gpu(dev, t, lo, hi, rank, world, local_rank):
     """One process per GPU (torchrun): every rank scans a cost-balanced contiguous slice of the centres,
-    one gather brings the rows to rank 0 (sharding.py).  NCCL when every rank has its own GPU, else gloo
-    over host tensors (several ranks sharing one device, e.g. in tests).  Returns the five result
-    arrays on rank 0 and None elsewhere."""
+    one gather brings the rows to rank 0 (sharding.py).  When every rank of the node has its own GPU the rows
+    stay on the device from the scan kernel to the NCCL gather (``DeviceScan.run_device``); when several ranks
+    share one device (tests on a one-GPU box) the gather runs over gloo on host tensors.  Returns the five
+    result arrays on rank 0 and None elsewhere."""
     import torch
     import torch.distributed as dist
     from . import sharding
-    from .native import device_count
-    own_gpu = device_count() >= world
+    own_gpu = ranks_own_a_gpu()
     started = not dist.is_initialized()
     if started:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29500')
-        dist.init_process_group('nccl' if own_gpu else 'gloo', rank=rank, world_size=world)
-    where = torch.device('cuda', local_rank) if own_gpu else torch.device('cpu')
+        if own_gpu:
+            torch.cuda.set_device(dev.scanner.device)
+            dist.init_process_group('nccl', rank=rank, world_size=world,
+                                    device_id=torch.device('cuda', dev.scanner.device))
+        else:
+            dist.init_process_group('gloo', rank=rank, world_size=world)
 
-    def scan_fn(ts, los, his):
-        T, iA, ix, ia, ns = dev.run(ts, los, his)
-        return tuple(torch.from_numpy(np.ascontiguousarray(a)).to(where) for a in (T, iA, ix, ia, ns))
+    if own_gpu:
+        where = torch.device('cuda', dev.scanner.device)
 
+        def scan_fn(ts, los, his):
+            return dev.run_device(ts, los, his, torch, where)
+    else:
+        def scan_fn(ts, los, his):
+            return tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in dev.run(ts, los, his))
+
+    ok = False
     try:
         got = sharding.scan_sharded(dev.problem.genpos, dev.problem.A, t, lo, hi, rank, world, scan_fn, dist, torch)
+        ok = True
         return None if got is None else tuple(a.cpu().numpy() for a in got)
     finally:
         if started:
-            dist.barrier()
+            if ok:                      # a rank that failed must not wait for the others (they would hang with it)
+                dist.barrier()
             dist.destroy_process_group()
 
 
@@ -136,6 +188,10 @@ class Scan:
         plan = windows.make_plan(InputData, fixSize=fixSize, r=r, s=s, phys=phys, noCenter=noCenter)
         if rank == 0:
             print('writing output to %s' % (outfile))
+            # the reference opens the output before it computes anything (v1:516,551,582,600): a bad path
+            # must fail now, not after the scan
+            with open(outfile, 'w'):
+                pass
         if world > 1:
             from .native import device_count
             device = local_rank % max(1, device_count())

@@ -85,7 +85,8 @@ def scan_sharded(genpos, A, t, lo, hi, rank, world, scan_fn, dist, torch):
 
     `scan_fn(t, lo, hi)` scans a contiguous slice of the centre list on this rank's device and
     returns torch tensors (T float64, iA, ix, ia, nsites int32) living on that device (the
-    product passes a closure over ``Scanner.scan_device``; CPU tests pass the oracle).
+    product passes ``DeviceScan.run_device``, i.e. ``blmx_scan_device`` on torch's current stream, so the
+    rows never leave the GPU before the gather; CPU tests pass the oracle).
     Returns the five gathered tensors on rank 0 (in centre order) and None elsewhere.
     """
     costs = centre_costs(genpos, t, lo, hi, A)

@@ -12,7 +12,11 @@ whole genome with the CLI's own --step flag: every S-th informative site is a ce
 the full 10 M-site data, exactly like `-s S` in the reference (v1:603-608).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo, CUDA
-    python bench.py --impl reference [...]                        # CPU arm (oracle port, all threads)
+    python bench.py --impl reference [...]                        # CPU arm: the reference's own path on host cores
+                                                                  # (C port on every step + the unmodified script once)
+
+Every CUDA run carries a parity gate: rows of the timed scan are compared with the CPU oracle
+(`parity` in the JSON line) and the run fails on a mismatch.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -174,6 +178,11 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def host_threads():
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1: not a limit on what the box has)."""
+    return len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+
+
 def cpu_sample_size(problems, plans, threads, target_s=15.0):
     """Centres for about `target_s` seconds of CPU work on this host: time two centres first
     (an interior centre of the 10 M-site workload is 6.6e8 log evaluations, parallelised over
@@ -196,18 +205,82 @@ def cpu_sample(problems, plans, n_centres, threads):
     return sample
 
 
-def run_cpu_oracle(problems, plans, sample, threads):
-    """Literal calcBaller (oracle/oracle_c.c, OpenMP) on the sample -> (seconds, centres, site pairs)."""
+def run_cpu_oracle(problems, plans, sample, threads, report_all=False, keep=None):
+    """Literal calcBaller (oracle/oracle_c.c, OpenMP) on the sample -> (seconds, centres, site pairs).
+    `keep`: a list that receives (chromosome, centre indices, oracle result) per chromosome."""
     from oracle import oracle_c
     t0 = time.perf_counter()
     centres = pairs = 0
     for c, idx in sample:
         p = problems[c]
         t, lo, hi = plans[c]
-        res = oracle_c.scan(p.genpos, p.cls, p.G, p.SP, p.A, t[idx], lo[idx], hi[idx], n_threads=threads)
+        res = oracle_c.scan(p.genpos, p.cls, p.G, p.SP, p.A, t[idx], lo[idx], hi[idx], n_threads=threads,
+                            report_all=report_all)
         centres += len(idx)
         pairs += res[4]
+        if keep is not None:
+            keep.append((c, idx, res))
     return time.perf_counter() - t0, centres, pairs
+
+
+def parity_sample(plans, T_rows, n_positive=64, n_any=32):
+    """Centres for the parity gate, chosen from the rows of the timed scan: `n_positive` centres whose
+    row carries a real maximum (T > 0; neutral synthetic data gives the all-zero row for most centres)
+    and `n_any` centres spread evenly whatever their row."""
+    sizes = np.array([len(p[0]) for p in plans])
+    bounds = np.concatenate(([0], np.cumsum(sizes)))
+    pos = np.flatnonzero(T_rows > 0)
+    picks = set(np.linspace(0, bounds[-1] - 1, n_any).astype(np.int64).tolist())
+    if len(pos):
+        picks |= set(pos[np.linspace(0, len(pos) - 1, min(n_positive, len(pos))).astype(np.int64)].tolist())
+    picks = np.array(sorted(picks), dtype=np.int64)
+    sample = []
+    for c in range(len(plans)):
+        mine = picks[(picks >= bounds[c]) & (picks < bounds[c + 1])] - bounds[c]
+        if len(mine):
+            sample.append((c, mine))
+    return sample, bounds
+
+
+def parity_check(problems, kept, bounds, rows, rows_all):
+    """Compare GPU rows (global centre order) with the oracle results `kept` -> the `parity` object.
+    rows = (T, iA, ix, ia, ns) of the timed scan (the reference's rule, T > 0 only); rows_all = the same
+    centres scanned with option report_all (oracle run the same way), so every compared centre carries a
+    real T and argmax."""
+    out = {'centres': 0, 'rows_T_gt_0': 0, 'max_rel_dT': 0.0, 'argmax_mismatch': 0, 'nsites_mismatch': 0,
+           'tolerance': '|dT| <= 1e-9*max(|T|,1); identical (A, x, a) and nSites'}
+    for which, (res_list, got) in (('', (kept[0], rows)), ('_report_all', (kept[1], rows_all))):
+        if got is None:
+            continue
+        n = pos = bad_arg = bad_ns = 0
+        worst = 0.0
+        k = 0
+        for c, idx, (rT, rA, rxa, rn, _) in res_list:
+            n_a = problems[c].n_a
+            if which:
+                sel = slice(k, k + len(idx))
+                k += len(idx)
+            else:
+                sel = bounds[c] + idx
+            T, iA, ix, ia, ns = (np.asarray(a)[sel] for a in got)
+            xa = np.where(iA >= 0, ix * n_a + ia, -1)
+            rel = np.abs(T - rT) / np.maximum(np.abs(rT), 1.)
+            worst = max(worst, float(rel.max()))
+            bad_arg += int(np.sum((iA != rA) | (xa != rxa)))
+            bad_ns += int(np.sum(ns != rn))
+            n += len(idx)
+            pos += int(np.sum(rA >= 0))
+        if which:
+            out['report_all'] = {'centres': n, 'rows_with_T': pos, 'max_rel_dT': worst,
+                                 'argmax_mismatch': bad_arg, 'nsites_mismatch': bad_ns}
+        else:
+            out.update({'centres': n, 'rows_T_gt_0': pos, 'max_rel_dT': worst, 'argmax_mismatch': bad_arg,
+                        'nsites_mismatch': bad_ns})
+    ra = out.get('report_all', {})
+    out['ok'] = bool(out['max_rel_dT'] <= 1e-9 and out['argmax_mismatch'] == 0 and out['nsites_mismatch'] == 0
+                     and ra.get('max_rel_dT', 0.0) <= 1e-9 and ra.get('argmax_mismatch', 0) == 0
+                     and ra.get('nsites_mismatch', 0) == 0)
+    return out
 
 
 def run_numpy_oracle_one_centre(problems, plans):
@@ -233,15 +306,87 @@ def run_numpy_oracle_one_centre(problems, plans):
             'sample': f'1 interior centre, {n_grid} grid points, numpy restatement (oracle/oracle_np.py), {secs:.1f} s'}
 
 
+# ------------------------------------------------------ the unmodified reference script
+REF_SCRIPT = os.path.join(ROOT, 'oracle', '_ref', 'BalLeRMix+_v1.py')     # copied there by oracle/make_ref.sh
+
+
+def write_reference_inputs(prefix, chrom):
+    """One synthetic chromosome as the reference's own input + --spect helper files."""
+    n = chrom['n']
+    with open(prefix + '.txt', 'w') as fh:
+        fh.write('physPos\tgenPos\tx\tn\n')
+        for pos, k in zip(chrom['pos'].tolist(), chrom['k'].tolist()):
+            fh.write(f'{pos}\t{pos * REC_RATE}\t{k}\t{n}\n')
+    cnt = np.bincount(chrom['k'], minlength=n + 1)
+    with open(prefix + '_spect.txt', 'w') as fh:
+        for k in np.flatnonzero(cnt):
+            fh.write('%s\t%s\t%s\n' % (k, n, cnt[k] / float(len(chrom['k']))))
+
+
+def run_reference_script(cores, n_sites=3000, centres_per_proc=2):
+    """the reference as shipped (BalLeRMix+_v1.py, numpy/scipy, single-threaded, no shard
+    flag), one unmodified process per host core, each on its own synthetic chromosome of the bench shape
+    (n = 200, same generator, same 100 x 10 x 51 grid passed as --listA because the reference's --rangeA
+    raises TypeError, v1:169-171) with `-s` chosen for `centres_per_proc` centres.  Returns the
+    cpu_baseline_reference object, or why it could not run."""
+    if not os.path.exists(REF_SCRIPT):
+        return {'kind': 'reference', 'unavailable': 'oracle/_ref/BalLeRMix+_v1.py missing (run oracle/make_ref.sh '
+                                                    'where /root/reference exists)'}
+    lo_a, hi_a, step_a = (float(v) for v in RANGE_A.split(','))
+    list_a = ','.join(str(lo_a + step_a * i) for i in range(int((hi_a - lo_a) / step_a) + 1))
+    n_A = list_a.count(',') + 1
+    stride = n_sites // centres_per_proc
+    work = tempfile.mkdtemp(prefix='blmx_ref_')
+    procs = []
+    site_evals = 0
+    t0 = time.perf_counter()
+    for p in range(cores):
+        chrom = make_chromosome(n_sites, seed=777 + p)
+        prefix = os.path.join(work, f'c{p}')
+        write_reference_inputs(prefix, chrom)
+        g = chrom['pos'] * REC_RATE
+        for c in range(0, n_sites, stride):
+            for a in list_a.split(','):
+                al = np.exp(-float(a) * np.abs(g - g[c]))
+                site_evals += int(np.sum((al >= 1e-8) & (g != g[c]))) * 510
+        cmd = [sys.executable, REF_SCRIPT, '-i', prefix + '.txt', '--spect', prefix + '_spect.txt', '-o',
+               prefix + '_out.txt', '--usePhysPos', '--rec', str(REC_RATE), '--listA', list_a, '-s', str(stride)]
+        env = dict(os.environ, OMP_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1', MKL_NUM_THREADS='1')
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, cwd=work))
+    t_launch = time.perf_counter()
+    rcs = [q.wait() for q in procs]
+    secs = time.perf_counter() - t_launch
+    rows = 0
+    for p in range(cores):
+        try:
+            with open(os.path.join(work, f'c{p}_out.txt')) as fh:
+                rows += max(0, len(fh.read().splitlines()) - 1)
+        except OSError:
+            pass
+    if any(rcs) or rows == 0:
+        return {'kind': 'reference', 'unavailable': f'reference script exited with {rcs[:4]}..., {rows} rows'}
+    n_grid = n_A * 510
+    return {
+        'kind': 'reference', 'cores': cores, 'processes': cores, 'centres': rows, 'seconds': secs,
+        's_per_centre': secs * cores / rows, 'value': rows * n_grid / secs, 'unit': 'centre*gridpoint/s',
+        'site_evals_per_s': site_evals / secs, 'site_evals_per_s_per_core': site_evals / secs / cores,
+        'sample': f'unmodified BalLeRMix+_v1.py (copied to oracle/_ref by oracle/make_ref.sh), {cores} concurrent '
+                  f'single-threaded processes, each a {n_sites}-site synthetic chromosome (n = 200, bench generator), '
+                  f'-s {stride} ({centres_per_proc} centres), --listA = the bench A grid, {n_grid} grid points per '
+                  f'centre; wall {secs:.0f} s incl. the script\'s own table precompute; windows here hold <= {n_sites} '
+                  f'sites against 12 710 on average in the benchmark, so compare site_evals_per_s, not value',
+        'setup_s': t_launch - t0,
+    }
+
+
 # ---------------------------------------------------------------------------------- arms
 def reference_arm(opt, rank):
-    """CPU arm: the oracle's C port of calcBaller on all host threads (the reference itself is a
-    Python script that cannot travel to the GPU box; oracle/ is its restatement)."""
+    """CPU arm = the reference's own implementation of the path on the box's host cores: every step times the
+    C port of calcBaller (oracle/oracle_c.c, OpenMP on all cores) on a bounded sample of the workload; once
+    per run the unmodified script itself is timed beside it (cpu_baseline_reference)."""
     if rank != 0:
         return
-    from oracle import oracle_c
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    threads = min(threads, oracle_c.max_threads()) if oracle_c.max_threads() > 0 else threads
+    threads = host_threads()
     chroms = make_genome(opt.sites)
     problems = make_problem(chroms)
     stride = max(1, BASE_STRIDE // opt.gpus)
@@ -249,7 +394,7 @@ def reference_arm(opt, rank):
     n_grid = problems[0].n_x * problems[0].n_a * len(problems[0].A)
     per_step = opt.cpu_centres or cpu_sample_size(problems, plans, threads, target_s=12.0)
     sample = cpu_sample(problems, plans, per_step, threads)
-    for _ in range(opt.warmup):
+    for _ in range(min(opt.warmup, 2)):
         run_cpu_oracle(problems, plans, cpu_sample(problems, plans, 1, threads), threads)
     secs = centres = pairs = 0
     for _ in range(opt.steps):
@@ -264,10 +409,20 @@ def reference_arm(opt, rank):
         'config': workload_config(opt, stride, problems, plans),
         'cpu_baseline': {'value': value, 'unit': 'centre*gridpoint/s', 'cores': threads, 'kind': 'port',
                          'sample': f'{per_step} centres per step spread evenly over the genome, all '
-                                   f'{n_grid} grid points each, literal calcBaller in C (oracle/oracle_c.c), OpenMP',
+                                   f'{n_grid} grid points each, literal calcBaller in C (oracle/oracle_c.c), '
+                                   f'OpenMP on {threads} threads',
                          'site_evals_per_s': pairs * problems[0].n_x * problems[0].n_a / secs},
         'e2e': {'value': value, 'unit': 'centre*gridpoint/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
+    if not opt.no_ref_script:
+        ref = run_reference_script(threads)
+        if 'site_evals_per_s' in ref:
+            # the script's rate on the benchmark's own windows: its cost is per site-evaluation
+            mean_w = pairs / max(1, centres * len(problems[0].A))
+            ref['value_at_bench_windows'] = ref['site_evals_per_s'] / mean_w
+            ref['note'] = ('value_at_bench_windows = site_evals_per_s / (mean sites per (centre, A) of the benchmark, '
+                           f'{mean_w:.0f}): the extrapolation to the 10 M-site windows, reported separately')
+        line['cpu_baseline_reference'] = ref
     print(json.dumps(line), flush=True)
 
 
@@ -284,6 +439,31 @@ def workload_config(opt, stride, problems, plans):
     }
 
 
+class Shard:
+    """This rank's cost-balanced contiguous slice of the centre list for one centre stride, with the
+    device buffers of a step."""
+
+    def __init__(self, problems, stride, rank, world, torch, dev, sharding):
+        self.plans = plan_centres(problems, stride)
+        costs = np.concatenate([sharding.centre_costs(p.genpos, pl[0], pl[1], pl[2], p.A)
+                                for p, pl in zip(problems, self.plans)])
+        parts = sharding.partition(costs, world)
+        self.counts = [e - b for b, e in parts]
+        begin, end = parts[rank]
+        self.offs = np.concatenate(([0], np.cumsum([len(pl[0]) for pl in self.plans])))
+        self.mine = []           # (chromosome, slice into its plan)
+        for c in range(len(self.plans)):
+            b, e = max(begin, self.offs[c]), min(end, self.offs[c + 1])
+            if e > b:
+                self.mine.append((c, slice(int(b - self.offs[c]), int(e - self.offs[c]))))
+        self.begin, self.n_mine, self.total = int(begin), int(end - begin), int(self.offs[-1])
+        host_in = {c: tuple(np.ascontiguousarray(a[sl]) for a in self.plans[c]) for c, sl in self.mine}
+        self.pinned = {c: tuple(torch.from_numpy(a).pin_memory() for a in host_in[c]) for c in host_in}
+        self.d_in = {c: tuple(x.to(dev) for x in self.pinned[c]) for c in self.pinned}
+        self.d_T = torch.zeros(self.n_mine, dtype=torch.float64, device=dev)
+        self.d_idx = [torch.zeros(self.n_mine, dtype=torch.int32, device=dev) for _ in range(4)]
+
+
 def cuda_arm(opt, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -298,49 +478,51 @@ def cuda_arm(opt, rank, world, local_rank):
     problems = make_problem(chroms)
     del chroms
     stride = max(1, BASE_STRIDE // world)
-    plans = plan_centres(problems, stride)
     n_xa = problems[0].n_x * problems[0].n_a
     n_A = len(problems[0].A)
     n_grid = n_xa * n_A
+    shard = Shard(problems, stride, rank, world, torch, dev, sharding)
+    plans, mine, counts, total_centres, n_mine = shard.plans, shard.mine, shard.counts, shard.total, shard.n_mine
 
-    # cost-balanced contiguous shard of the global centre list
-    costs = np.concatenate([sharding.centre_costs(p.genpos, pl[0], pl[1], pl[2], p.A)
-                            for p, pl in zip(problems, plans)])
-    parts = sharding.partition(costs, world)
-    counts = [e - b for b, e in parts]
-    begin, end = parts[rank]
-    offs = np.concatenate(([0], np.cumsum([len(pl[0]) for pl in plans])))
-    mine = []        # (chromosome, slice into its plan)
-    for c in range(len(plans)):
-        b, e = max(begin, offs[c]), min(end, offs[c + 1])
-        if e > b:
-            mine.append((c, slice(int(b - offs[c]), int(e - offs[c]))))
-    n_mine = end - begin
-    total_centres = int(offs[-1])
-
-    # resident problems + device buffers
+    # resident problems: one handle per chromosome this rank touches
     scanners = {}
     for c, _ in mine:
         scanners[c] = native.Scanner(device=local_rank, group=opt.group, farfield=opt.farfield).load(problems[c])
         scanners[c].set_option('timing', 1)
-    stream = torch.cuda.current_stream().cuda_stream
-    host_in = {c: tuple(np.ascontiguousarray(a[sl]) for a in plans[c]) for c, sl in mine}
-    pinned = {c: tuple(torch.from_numpy(a).pin_memory() for a in host_in[c]) for c in host_in}
-    d_in = {c: tuple(x.to(dev) for x in pinned[c]) for c in pinned}
-    d_T = torch.zeros(n_mine, dtype=torch.float64, device=dev)
-    d_idx = [torch.zeros(n_mine, dtype=torch.int32, device=dev) for _ in range(4)]
+    info = [scanners[c].problem_info() for c, _ in mine]
+    main_stream = torch.cuda.current_stream()
+    # chromosomes are independent launches: issued round-robin on a few streams so that the tail of one
+    # launch (its last, cheapest work items) overlaps the head of the next
+    side = [torch.cuda.Stream(device=dev) for _ in range(max(1, opt.streams))]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def scan_resident():
+    def scan_into(sh, reload_problem=False):
+        """One step on this rank: every chromosome of the shard, then pack + gather (the only collective)."""
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
         o = 0
-        for c, _ in mine:
-            t, lo, hi = d_in[c]
-            n = t.shape[0]
-            scanners[c].scan_device(n, t.data_ptr(), lo.data_ptr(), hi.data_ptr(), d_T[o:].data_ptr(),
-                                    *[x[o:].data_ptr() for x in d_idx], stream=stream)
+        for k, (c, _) in enumerate(sh.mine):
+            st = side[k % len(side)]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                if reload_problem:
+                    scanners[c].load(problems[c])               # H2D of sites + tables, class sort, block moments
+                    t, lo, hi = (x.to(dev, non_blocking=True) for x in sh.pinned[c])   # H2D of the centres
+                else:
+                    t, lo, hi = sh.d_in[c]
+                n = t.shape[0]
+                scanners[c].scan_device(n, t.data_ptr(), lo.data_ptr(), hi.data_ptr(), sh.d_T[o:].data_ptr(),
+                                        *[x[o:].data_ptr() for x in sh.d_idx], stream=st.cuda_stream)
+                if reload_problem:
+                    for x in (t, lo, hi):
+                        x.record_stream(st)
             o += n
-        rows = sharding.pack_rows(d_T, *d_idx, torch)
-        return sharding.gather_rows(rows, counts, rank, world, dist, torch)
+        for st in side:
+            join = torch.cuda.Event()
+            join.record(st)
+            main_stream.wait_event(join)
+        rows = sharding.pack_rows(sh.d_T, *sh.d_idx, torch)
+        return sharding.gather_rows(rows, sh.counts, rank, world, dist, torch)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -348,123 +530,112 @@ def cuda_arm(opt, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing -------------------------------------------------------
-    for _ in range(opt.warmup):
-        scan_resident()
-        flush.zero_()
-    sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    def collect():
+    def collect(sh):
         """Per-launch kernel events and work counters of the LAST step, summed over this rank's scanners."""
         tot = {'pairs': 0, 'single': 0, 'far_blocks': 0, 'far_terms': 0, 'far_sites': 0, 'edge_sites': 0,
                'quads': 0, 'launches': 0}
         k_ms, k_n = 0.0, 0
-        for c, _ in mine:
+        for c, _ in sh.mine:
             kms, kn = scanners[c].kernel_ms()
             k_ms += kms; k_n += kn
             for key, v in scanners[c].counters_all().items():
                 tot[key] = tot.get(key, 0) + v
         return tot, k_ms, k_n
 
-    sync_all()
-    e0.record()
-    for _ in range(opt.steps):
-        gathered = scan_resident()
+    def timed(fn, steps, flush_l2=True):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+            if flush_l2:
+                flush.zero_()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
+        return ms, out
+
+    def reduce_sum(values):
+        if world == 1:
+            return [float(v) for v in values]
+        agg = torch.tensor([float(v) for v in values], dtype=torch.float64, device=dev)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        return agg.tolist()
+
+    # ---- device-resident timing -------------------------------------------------------
+    for _ in range(opt.warmup):
+        scan_into(shard)
         flush.zero_()
-    e1.record()
     sync_all()
-    ms = e0.elapsed_time(e1)
-    cnt, kernel_ms, kernel_launches = collect()
-    pairs, single, lib_launches = cnt['pairs'], cnt['single'], cnt['launches']
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, gathered = timed(lambda: scan_into(shard), opt.steps)
+    cnt, kernel_ms, kernel_launches = collect(shard)
     clocks = sampler.stop() if rank == 0 else None
+    pairs_all, launches_all = (int(v) for v in reduce_sum([cnt['pairs'], cnt['launches']]))
+    value = total_centres * n_grid * opt.steps / (ms * 1e-3)
+    resident_rows = sharding.unpack_rows(gathered.cpu(), torch) if rank == 0 else None
 
     # the same workload with every site evaluated directly (option farfield = 0): the FP64-bound kernel
     direct = None
-    if opt.farfield and world == 1:
+    if opt.farfield and world == 1 and not opt.profile:
         for c, _ in mine:
             scanners[c].set_option('farfield', 0)
-        scan_resident()
-        sync_all()
-        e0.record()
-        scan_resident()
-        e1.record()
-        sync_all()
-        d_ms = e0.elapsed_time(e1)
-        d_cnt, d_kms, d_kn = collect()
+        scan_into(shard)
+        d_ms, _ = timed(lambda: scan_into(shard), 1, flush_l2=False)
+        d_cnt, d_kms, d_kn = collect(shard)
         direct = (d_ms, d_cnt, d_kms, d_kn)
         for c, _ in mine:
             scanners[c].set_option('farfield', 1)
-    if world > 1:
-        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-        agg = torch.tensor([pairs, single, lib_launches, kernel_ms, kernel_launches], dtype=torch.float64, device=dev)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        pairs_all, single_all, launches_all = int(agg[0].item()), int(agg[1].item()), int(agg[2].item())
-    else:
-        pairs_all, single_all, launches_all = pairs, single, lib_launches
-    value = total_centres * n_grid * opt.steps / (ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ---------------------------------
-    def scan_e2e():
-        o = 0
-        for c, _ in mine:
-            scanners[c].load(problems[c])                       # H2D of sites + tables, class sort
-            t, lo, hi = (x.to(dev, non_blocking=True) for x in pinned[c])   # H2D of the centres
-            n = t.shape[0]
-            scanners[c].scan_device(n, t.data_ptr(), lo.data_ptr(), hi.data_ptr(), d_T[o:].data_ptr(),
-                                    *[x[o:].data_ptr() for x in d_idx], stream=stream)
-            o += n
-        rows = sharding.pack_rows(d_T, *d_idx, torch)
-        g = sharding.gather_rows(rows, counts, rank, world, dist, torch)
-        return g.cpu() if g is not None else None                 # D2H of every row on rank 0
+    e2e = None
+    if not opt.profile:
+        def scan_e2e():
+            g = scan_into(shard, reload_problem=True)
+            return g.cpu() if g is not None else None                 # D2H of every row on rank 0
+        scan_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_ms, host_rows = timed(scan_e2e, opt.steps, flush_l2=False)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            tmax = torch.tensor([wall_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            wall_ms = float(tmax.item())
+        e2e_ms = max(e2e_ms, wall_ms)
+        h2d = sum(problems[c].h2d_bytes + 24 * (sl.stop - sl.start) for c, sl in mine)
+        d2h = 24 * total_centres if rank == 0 else 0
+        h2d, d2h = (int(v) for v in reduce_sum([h2d, d2h]))
+        e2e = {'value': total_centres * n_grid * opt.steps / (e2e_ms * 1e-3), 'unit': 'centre*gridpoint/s',
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / opt.steps,
+               'includes': 'blmx_load of every chromosome (H2D of sites and tables, device class sort, far-field '
+                           'block moments), H2D of the centres, scan, gather, D2H of every row'}
+        if rank == 0:
+            er = sharding.unpack_rows(host_rows, torch)
+            same = all(bool((a == b).all()) for a, b in zip(er, resident_rows))
+            e2e['rows_equal_resident_run'] = same
 
-    scan_e2e()
-    sync_all()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(opt.steps):
-        host_rows = scan_e2e()
-    e1.record()
-    sync_all()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    if world > 1:
-        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tmax.item())
-    h2d = sum(problems[c].h2d_bytes + 24 * (sl.stop - sl.start) for c, sl in mine)
-    d2h = 24 * total_centres if rank == 0 else 0
-    if world > 1:
-        agg = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-        h2d, d2h = int(agg[0].item()), int(agg[1].item())
-    e2e_value = total_centres * n_grid * opt.steps / (e2e_ms * 1e-3)
+    # ---- strong scaling: the SAME centre list (stride 128) whatever the number of GPUs ----------
+    strong = None
+    if opt.strong_stride > 0 and not opt.profile:
+        sh2 = Shard(problems, opt.strong_stride, rank, world, torch, dev, sharding)
+        scan_into(sh2)
+        s_ms, _ = timed(lambda: scan_into(sh2), opt.strong_steps)
+        strong = {'centre_stride': opt.strong_stride, 'centres_per_step': sh2.total, 'steps': opt.strong_steps,
+                  'ms_per_step': s_ms / opt.strong_steps, 'value': sh2.total * n_grid * opt.strong_steps / (s_ms * 1e-3),
+                  'unit': 'centre*gridpoint/s', 'scaling': 'strong',
+                  'note': 'total work fixed for every N (the weak-scaling headline divides the stride by N)'}
+        del sh2
 
+    # ---- parity gate (rank 0): rows of the timed run against the CPU oracle ----------------
     if rank == 0:
-        # sanity: the gathered rows are complete and decoded
-        T, iA, ix, ia, ns = sharding.unpack_rows(host_rows, torch)
-        assert T.shape[0] == total_centres and bool((iA >= -1).all()) and bool((ns >= 0).all())
-
-        peak_tf, peak_mhz = native.measure_fp64_peak(local_rank, 0.5)
-        n_items = n_mine * n_A
-        flops = algorithmic_flops(cnt, n_xa, n_items)
-        k_s = kernel_ms * 1e-3
-        achieved = flops / k_s / 1e12 if k_s > 0 else None
-        table_bytes = 8.0 * n_xa * problems[0].G.shape[0] * n_items          # D rows a warp may touch
-        site_bytes = 8.0 * pairs
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get('dram_bytes_per_launch')
-        hbm_peak = None
-        mp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-        if os.path.exists(mp):
-            with open(mp) as fh:
-                hbm_peak = json.load(fh).get('hbm_gbs')
         line = {
             'metric': 'centres x grid-points / s (B2 scan)', 'value': value, 'unit': 'centre*gridpoint/s',
             'n_gpus': world, 'steps': opt.steps, 'warmup': opt.warmup, 'ms_per_step': ms / opt.steps,
@@ -472,30 +643,88 @@ def cuda_arm(opt, rank, world, local_rank):
             'config': workload_config(opt, stride, problems, plans),
             'site_evals_per_s': pairs_all * n_xa / (ms / opt.steps * 1e-3),
             'mean_sites_per_centre_A': pairs_all / max(1, total_centres * n_A),
-            'e2e': {'value': e2e_value, 'unit': 'centre*gridpoint/s', 'h2d_bytes_per_step': int(h2d),
-                    'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms / opt.steps},
             'gpu_launches': int(launches_all * opt.steps),
             'clocks': clocks,
-            'roofline': {
-                'bound': 'fp64', 'kernel': 'scan_kernel<16,%d,%s>' % (opt.group, 'far' if opt.farfield else 'direct'),
-                'achieved': achieved,
-                'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved and peak_tf else None,
-                'peak_source': 'measured live: register-resident DFMA loop (blmx_measure_fp64_peak); '
-                               'MEASURED_PEAKS.json has no FP64 entry',
-                'peak_nominal': FP64_NOMINAL_TFLOPS,
-                'frac_of_nominal': (achieved / FP64_NOMINAL_TFLOPS) if achieved else None,
-                'kernel_ms_per_launch': kernel_ms / max(1, kernel_launches), 'launches_timed': kernel_launches,
-                'algorithmic_flops_per_launch': flops / max(1, kernel_launches),
-                'sites_single_frac': single / max(1, pairs), 'sites_far_frac': cnt['far_sites'] / max(1, pairs),
-                'traffic': traffic,
-                'hbm': {'algorithmic_bytes_per_launch': (site_bytes + table_bytes) / max(1, kernel_launches),
-                        'achieved_gbs': (site_bytes + table_bytes) / k_s / 1e9 if k_s > 0 else None,
-                        'peak_gbs': hbm_peak,
-                        'note': 'upper bound (every class row counted); the path is FP64-bound'},
-            },
         }
-        line['mode'] = ('farfield: far sites through power sums of alpha (DESIGN.md §3.4)' if opt.farfield
-                        else 'direct: every site evaluated per grid point')
+        if e2e is not None:
+            line['e2e'] = e2e
+        if strong is not None:
+            line['strong'] = strong
+
+        threads = host_threads()
+        cpu = None
+        if not opt.no_cpu:
+            T_rows = resident_rows[0].numpy()
+            sample, bounds = parity_sample(plans, T_rows, opt.parity_positive, opt.parity_any)
+            kept = ([], [])
+            secs, centres, cpairs = run_cpu_oracle(problems, plans, sample, threads, keep=kept[0])
+            run_cpu_oracle(problems, plans, sample, threads, report_all=True, keep=kept[1])
+            # the same centres with option report_all on the GPU (this rank's device, outside the timed region)
+            got_all = [[] for _ in range(5)]
+            for c, idx in sample:
+                t, lo, hi = plans[c]
+                with native.Scanner(device=local_rank, group=opt.group, farfield=opt.farfield) as sc:
+                    sc.set_option('report_all', 1)
+                    sc.load(problems[c])
+                    for k, a in enumerate(sc.scan(t[idx], lo[idx], hi[idx])):
+                        got_all[k].append(a)
+            rows_all = tuple(np.concatenate(a) for a in got_all)
+            rows_np = tuple(a.numpy() for a in resident_rows)
+            line['parity'] = parity_check(problems, kept, bounds, rows_np, rows_all)
+            line['parity']['checker'] = 'oracle/oracle_c.c (literal calcBaller, compensated sums)'
+            cpu = {'value': centres * n_grid / secs, 'unit': 'centre*gridpoint/s', 'cores': threads, 'kind': 'port',
+                   'sample': f'{centres} centres of the timed scan ({line["parity"]["rows_T_gt_0"]} with T > 0, the '
+                             f'rest spread evenly), all {n_grid} grid points each, literal calcBaller in C '
+                             f'(oracle/oracle_c.c), OpenMP on {threads} threads, {secs:.1f} s',
+                   'site_evals_per_s': cpairs * n_xa / secs}
+
+        peak_tf, peak_mhz = native.measure_fp64_peak(local_rank, 0.5)
+        n_items = n_mine * n_A
+        flops = algorithmic_flops(cnt, n_xa, n_items)
+        k_s = kernel_ms * 1e-3
+        achieved = flops / k_s / 1e12 if k_s > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh)
+        hbm_peak = None
+        mp = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(mp):
+            with open(mp) as fh:
+                hbm_peak = json.load(fh).get('hbm_gbs')
+        n_sites_mine = sum(len(problems[c].genpos) for c, _ in mine)
+        moment_bytes = sum(i['moment_bytes'] for i in info)
+        # HBM bytes one launch must move at least once: the chromosome's site arrays (g, gs: 8 B, is: 4 B per
+        # site), the R table, its far-field block moments, and the (centre, A) candidates written and re-read
+        hbm_algo = (20.0 * n_sites_mine + 8.0 * 512 * len(problems[0].G) * len(mine) + moment_bytes
+                    + 2 * 16.0 * n_items) / max(1, kernel_launches)
+        line['roofline'] = {
+            'bound': 'fp64', 'kernel': 'scan_kernel<16,%d,%s>' % (opt.group, 'far' if opt.farfield else 'direct'),
+            'achieved': achieved,
+            'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': (achieved / peak_tf) if achieved and peak_tf else None,
+            'peak_source': 'measured live: register-resident DFMA loop (blmx_measure_fp64_peak); '
+                           'MEASURED_PEAKS.json has no FP64 entry',
+            'peak_nominal': FP64_NOMINAL_TFLOPS,
+            'frac_of_nominal': (achieved / FP64_NOMINAL_TFLOPS) if achieved else None,
+            'kernel_ms_per_launch': kernel_ms / max(1, kernel_launches), 'launches_timed': kernel_launches,
+            'kernel_share_of_step': kernel_ms / (ms / opt.steps) if ms > 0 else None,
+            'timing': 'CUDA events recorded by the library around every scan_kernel launch of the last timed step, '
+                      f'on the launching stream; {len(side)} streams, so launches overlap at their tails and the '
+                      'summed durations slightly exceed the step',
+            'algorithmic_flops_per_launch': flops / max(1, kernel_launches),
+            'work': {k: cnt[k] for k in ('pairs', 'single', 'quads', 'far_sites', 'far_blocks', 'edge_sites', 'far_terms')},
+            'sites_far_frac': cnt['far_sites'] / max(1, cnt['pairs']),
+            'traffic': traffic.get('dram_bytes_per_launch') if traffic else None,
+            'traffic_source': traffic.get('source') if traffic else None,
+            'hbm': {'algorithmic_bytes_per_launch': hbm_algo,
+                    'achieved_gbs': hbm_algo / (k_s / max(1, kernel_launches)) / 1e9 if k_s > 0 else None,
+                    'peak_gbs': hbm_peak, 'moment_bytes_resident': moment_bytes,
+                    'note': 'bytes a launch must fetch from HBM at least once (site arrays, table, block moments, '
+                            'candidates); everything else is L2/L1 traffic. The path is FP64-bound.'},
+        }
+        line['mode'] = ('farfield: far sites through per-block precomputed power sums of alpha (DESIGN.md §3.4)'
+                        if opt.farfield else 'direct: every site evaluated per grid point')
         if direct is not None:
             d_ms, d_cnt, d_kms, d_kn = direct
             d_flops = algorithmic_flops(d_cnt, n_xa, n_items)
@@ -507,23 +736,21 @@ def cuda_arm(opt, rank, world, local_rank):
                              'kernel_ms_per_launch': d_kms / max(1, d_kn), 'launches_timed': d_kn,
                              'algorithmic_flops_per_launch': d_flops / max(1, d_kn)},
                 'note': 'same step with option farfield = 0 (one warm-up + one timed step)'}
-        if world == 1 and not opt.no_cpu:
-            threads = len(os.sched_getaffinity(0))
-            n_cpu = opt.cpu_centres or cpu_sample_size(problems, plans, threads)
-            sample = cpu_sample(problems, plans, n_cpu, threads)
-            secs, centres, cpairs = run_cpu_oracle(problems, plans, sample, threads)
-            line['cpu_baseline'] = {
-                'value': centres * n_grid / secs, 'unit': 'centre*gridpoint/s', 'cores': threads, 'kind': 'port',
-                'sample': f'{centres} centres spread evenly over the genome, all {n_grid} grid points each, '
-                          f'literal calcBaller in C (oracle/oracle_c.c), OpenMP on {threads} threads, {secs:.1f} s',
-                'site_evals_per_s': cpairs * n_xa / secs}
-            line['cpu_baseline_numpy'] = run_numpy_oracle_one_centre(problems, plans)
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+            if world == 1:
+                line['cpu_baseline_numpy'] = run_numpy_oracle_one_centre(problems, plans)
         print(json.dumps(line), flush=True)
+        parity_failed = 'parity' in line and not line['parity']['ok']
+    else:
+        parity_failed = False
     for s in scanners.values():
         s.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_failed:
+        sys.exit('bench: PARITY GATE FAILED (see "parity" in the JSON line)')
 
 
 def main():
@@ -536,8 +763,18 @@ def main():
     ap.add_argument('--group', type=int, default=4, choices=[1, 4])
     ap.add_argument('--farfield', type=int, default=1, choices=[0, 1],
                     help='1 (default): far sites enter through power sums; 0: every site evaluated directly')
-    ap.add_argument('--cpu-centres', type=int, default=0, help='centres in the CPU sample (default: one per thread)')
-    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--streams', type=int, default=2, help='CUDA streams the per-chromosome launches rotate over')
+    ap.add_argument('--strong-stride', type=int, default=128,
+                    help='centre stride of the fixed-work (strong scaling) leg; 0 = skip it')
+    ap.add_argument('--strong-steps', type=int, default=1)
+    ap.add_argument('--parity-positive', type=int, default=64, help='parity gate: centres whose row has T > 0')
+    ap.add_argument('--parity-any', type=int, default=32, help='parity gate: centres spread evenly')
+    ap.add_argument('--cpu-centres', type=int, default=0, help='reference arm: centres per step (default: ~12 s)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the parity gate and the cpu_baseline leg')
+    ap.add_argument('--no-ref-script', action='store_true',
+                    help='reference arm: skip the run of the unmodified script (oracle/_ref)')
+    ap.add_argument('--profile', action='store_true',
+                    help='only the device-resident timed steps (for ncu): no direct / e2e / strong legs')
     opt = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -547,6 +784,8 @@ def main():
         return
     if world != opt.gpus and world > 1:
         opt.gpus = world
+    if opt.profile:
+        opt.no_cpu = True
     cuda_arm(opt, rank, world, local_rank)
 
 

@@ -127,6 +127,10 @@ int blmx_scan_oneshot(int device, const blmx_problem *p, int64_t n_centres, cons
  *                site), taken from per-block moments that blmx_load precomputes (the value at the
  *                time of blmx_load decides whether they are built); 0 = every site is evaluated
  *                per grid point
+ *   "report_all" 0 (default) = the reference's rule, only a grid point with T > 0 is reported (v1:451,501);
+ *                1 = diagnostic: the best grid point is reported whatever the sign of T (the maximum
+ *                starts from -inf instead of 0), so that parity checks on neutral data compare a real
+ *                T and argmax on every centre instead of the all-zero row
  *   "batch"      centres per kernel launch (scratch = batch * n_A * 16 bytes)
  *   "timing"     1 = record CUDA events around every scan kernel (see blmx_last_kernel_ms)
  */

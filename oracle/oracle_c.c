@@ -46,11 +46,13 @@ static int64_t lower_bound(const double *a, int64_t n, double key) {
     return lo;
 }
 
-int oracle_scan(int64_t n_sites, const double *genpos, const int32_t *cls, int32_t n_classes,
-                const double *G, const double *SP, int32_t n_xa, int32_t n_A, const double *A,
-                int64_t n_centres, const double *t, const int64_t *lo, const int64_t *hi,
-                double *oT, int32_t *oiA, int32_t *oixa, int32_t *ons, int32_t n_threads,
-                uint64_t *site_pairs) {
+/* t_floor: the value a grid point must beat to be reported -- 0 in the reference (v1:451); -inf reports the
+ * best grid point of every centre whatever its sign (parity checks on neutral data, where most maxima are <= 0). */
+int oracle_scan_floor(int64_t n_sites, const double *genpos, const int32_t *cls, int32_t n_classes,
+                      const double *G, const double *SP, int32_t n_xa, int32_t n_A, const double *A,
+                      int64_t n_centres, const double *t, const int64_t *lo, const int64_t *hi,
+                      double *oT, int32_t *oiA, int32_t *oixa, int32_t *ons, int32_t n_threads,
+                      uint64_t *site_pairs, double t_floor) {
     int sorted = 1;
     for (int64_t i = 1; i < n_sites; ++i)
         if (!(genpos[i] >= genpos[i - 1])) { sorted = 0; break; }
@@ -113,7 +115,7 @@ int oracle_scan(int64_t n_sites, const double *genpos, const int32_t *cls, int32
                 }
                 pairs_total += (uint64_t)m;
                 const double cl_neut = neut.s + neut.c;
-                double bT = 0.0;
+                double bT = t_floor;
                 int bxa = -1;
                 if (m > 0) {                                             /* v1:458 */
                     for (int xa = 0; xa < n_xa; ++xa) {
@@ -132,18 +134,27 @@ int oracle_scan(int64_t n_sites, const double *genpos, const int32_t *cls, int32
     }
     /* v1:453,501: A in visiting order, strict '>' from Tmax = 0 */
     for (int64_t j = 0; j < n_centres; ++j) {
-        double bT = 0.0;
+        double bT = t_floor;
         int bA = -1, bxa = -1, bns = 0;
         for (int iA = 0; iA < n_A; ++iA) {
             const int64_t task = j * n_A + iA;
             if (cxa[task] >= 0 && cT[task] > bT) { bT = cT[task]; bA = iA; bxa = cxa[task]; bns = cns[task]; }
         }
-        oT[j] = bT; oiA[j] = bA; oixa[j] = bxa; ons[j] = bns;
+        oT[j] = bA >= 0 ? bT : 0.0; oiA[j] = bA; oixa[j] = bxa; ons[j] = bns;
     }
     free(cT); free(cxa); free(cns);
     free(logG);
     if (site_pairs) *site_pairs = pairs_total;
     return err ? -1 : 0;
+}
+
+int oracle_scan(int64_t n_sites, const double *genpos, const int32_t *cls, int32_t n_classes,
+                const double *G, const double *SP, int32_t n_xa, int32_t n_A, const double *A,
+                int64_t n_centres, const double *t, const int64_t *lo, const int64_t *hi,
+                double *oT, int32_t *oiA, int32_t *oixa, int32_t *ons, int32_t n_threads,
+                uint64_t *site_pairs) {
+    return oracle_scan_floor(n_sites, genpos, cls, n_classes, G, SP, n_xa, n_A, A, n_centres, t, lo, hi,
+                             oT, oiA, oixa, ons, n_threads, site_pairs, 0.0);
 }
 
 int oracle_max_threads(void) {

@@ -24,10 +24,10 @@ def lib():
         if not os.path.exists(_PATH):
             build()
         L = C.CDLL(_PATH)
-        L.oracle_scan.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                                  C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                  C.POINTER(C.c_uint64)]
+        L.oracle_scan_floor.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.POINTER(C.c_uint64), C.c_double]
         _lib = L
     return _lib
 
@@ -36,11 +36,13 @@ def max_threads():
     return lib().oracle_max_threads()
 
 
-def scan(genpos, cls, G, SP, A, t, lo, hi, n_threads=0):
+def scan(genpos, cls, G, SP, A, t, lo, hi, n_threads=0, report_all=False):
     """Literal calcBaller over a batch of centres.
 
     SP is [n_xa, n_classes]; returns (T, iA, ixa, nsites, site_pairs) with -1 indices
-    where no grid point has T > 0.
+    where no grid point has T > 0.  ``report_all``: start the maximum from -inf instead of the
+    reference's 0 (v1:451), i.e. report the best grid point even when its T <= 0 (the product's
+    diagnostic option of the same name).
     """
     genpos = np.ascontiguousarray(genpos, np.float64)
     cls = np.ascontiguousarray(cls, np.int32)
@@ -60,9 +62,9 @@ def scan(genpos, cls, G, SP, A, t, lo, hi, n_threads=0):
     def p(a):
         return a.ctypes.data_as(C.c_void_p)
 
-    rc = lib().oracle_scan(len(genpos), p(genpos), p(cls), len(G), p(G), p(SP), SP.shape[0], len(A), p(A),
-                           n, p(t), p(lo), p(hi), p(T), p(iA), p(ixa), p(ns), int(n_threads),
-                           C.byref(pairs))
+    rc = lib().oracle_scan_floor(len(genpos), p(genpos), p(cls), len(G), p(G), p(SP), SP.shape[0], len(A), p(A),
+                                 n, p(t), p(lo), p(hi), p(T), p(iA), p(ixa), p(ns), int(n_threads),
+                                 C.byref(pairs), -np.inf if report_all else 0.0)
     if rc != 0:
         raise MemoryError('oracle_scan failed')
     return T, iA, ixa, ns, pairs.value

@@ -93,7 +93,7 @@ def oracle_kwargs(argv):
     return kw
 
 
-def compare_scan(lines, golden_path, rtol=1e-9, max_near_ties=0):
+def compare_scan(lines, golden_path, rtol=1e-9, max_near_ties=0, tie_rows=None):
     """Compare output lines (None = row not evaluated) with a golden file.
 
     Every evaluated row must agree in the two position fields and in nSites-or-argmax as
@@ -101,6 +101,9 @@ def compare_scan(lines, golden_path, rtol=1e-9, max_near_ties=0):
     except for at most `max_near_ties` rows whose CLR still agrees within rtol -- two grid
     points whose T differ by less than the reference's own summation noise (SURVEY.md A.4:
     the reference's sum order is unspecified), which happens with the two-class B1 tables.
+    With ``tie_rows`` (a list) every such row is appended to it as (line number, got fields, golden fields)
+    (line 0 = header) instead of being counted against ``max_near_ties``: the caller then PROVES each one a tie with
+    ``assert_ties`` (literal T at both grid points).
     Returns (rows compared, rows byte-identical, max relative CLR difference, near ties).
     """
     with open(golden_path) as fh:
@@ -108,7 +111,7 @@ def compare_scan(lines, golden_path, rtol=1e-9, max_near_ties=0):
     assert len(gold) == len(lines), f'{len(lines)} rows, golden has {len(gold)}'
     n = same = ties = 0
     worst = 0.
-    for got, ref in zip(lines, gold):
+    for line_no, (got, ref) in enumerate(zip(lines, gold)):
         if got is None:
             continue
         n += 1
@@ -127,8 +130,55 @@ def compare_scan(lines, golden_path, rtol=1e-9, max_near_ties=0):
         worst = max(worst, rel)
         if a[3:] != b[3:]:
             ties += 1
-            assert ties <= max_near_ties, f'argmax differs:\n got {got!r}\n ref {ref!r}'
+            if tie_rows is not None:
+                tie_rows.append((line_no, a, b))
+            else:
+                assert ties <= max_near_ties, f'argmax differs:\n got {got!r}\n ref {ref!r}'
     return n, same, worst, ties
+
+
+def literal_T(prob, t, lo, hi, iA, xa):
+    """T of ONE grid point for one centre, the reference's formula term by term (v1:454-499) with exactly
+    rounded sums (math.fsum) -> (T, nSites)."""
+    import math
+    g = prob.genpos
+    idx = np.arange(max(int(lo), 0), min(int(hi), len(g) - 1) + 1)
+    al = np.exp(-prob.A[iA] * np.abs(g[idx] - t))
+    ok = (al >= 1e-8) & (g[idx] != t)
+    c, a = prob.cls[idx][ok], al[ok]
+    mix = a * prob.SP[xa, c] + (1. - a) * prob.G[c]
+    return 2 * (math.fsum(np.log(mix)) - math.fsum(np.log(prob.G[c]))), int(ok.sum())
+
+
+def assert_ties(argv, tie_rows, tol=1e-12):
+    """Every row whose argmax differs from the golden must be a genuine tie: the literal T at OUR grid point and
+    at the GOLDEN's grid point, for that row's centre and window, agree within tol*max(|T|, 1) -- i.e. within
+    the reference's own summation noise (its sum order is set-iteration order), so which of the
+    two wins is decided by rounding, not by the likelihood.  Returns the largest relative gap seen."""
+    from ballermixplus_b200 import windows
+    from ballermixplus_b200.problem import build_problem
+    opt, data, neutral, grid, sel = host_objects(argv)
+    prob, order = build_problem(data, neutral, sel, grid)
+    with quiet():
+        plan = windows.make_plan(data, fixSize=opt.size, r=opt.w, s=opt.step, phys=opt.phys, noCenter=opt.noCenter)
+    t, lo, hi, gap = plan.arrays()
+    text = {'A': [f'{v}' for v in order.A], 'x': [f'{v}' for v in order.x], 'a': [f'{v}' for v in order.a]}
+    worst = 0.
+    for row, got, ref in tie_rows:
+        j = row - 1                                   # line 0 is the header
+        vals = []
+        for f in (got, ref):
+            if f[3] == '0.0' and f[4] == '0.0' and f[5] == '0.0':          # the all-zero row: T = 0 by definition
+                vals.append(0.)
+                continue
+            iA, ix, ia = text['A'].index(f[5]), text['x'].index(f[3]), text['a'].index(f[4])
+            T, ns = literal_T(prob, t[j], lo[j], hi[j], iA, ix * prob.n_a + ia)
+            assert ns == int(float(f[6])), f'nSites differs from the literal count in row {row}: {f}'
+            vals.append(T)
+        gap_rel = abs(vals[0] - vals[1]) / max(abs(vals[1]), 1.)
+        assert gap_rel <= tol, f'row {row}: not a tie, literal T {vals[0]!r} vs {vals[1]!r}\n got {got}\n ref {ref}'
+        worst = max(worst, gap_rel)
+    return worst
 
 
 @contextlib.contextmanager
