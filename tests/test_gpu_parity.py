@@ -215,7 +215,86 @@ def test_synthetic_n200_against_oracle_sample():
         assert np.array_equal(a, b)
 
 
-def _cli_vs_oracle(argv, tmp_path, near_ties=0):
+def test_report_all_reports_the_best_grid_point_whatever_its_sign():
+    """Option report_all (the maximum starts from -inf instead of the reference's 0, v1:451): on neutral
+    synthetic data most centres have no grid point with T > 0, so the ordinary rows are all-zero and compare
+    nothing; with report_all every centre carries a real (negative) T, argmax and nSites, checked against
+    the oracle run the same way."""
+    import bench
+    from oracle import oracle_c
+    from ballermixplus_b200.native import Scanner
+    chrom = bench.make_chromosome(30000, seed=4)
+    prob = bench.make_problem([chrom])[0]
+    n = len(prob.genpos)
+    c = np.linspace(0, n - 1, 40).astype(np.int64)
+    t, lo, hi = prob.genpos[c], np.zeros(len(c), np.int64), np.full(len(c), n - 1, np.int64)
+    lo[3], hi[3] = 50, 40                                     # an empty window stays the all-zero row
+    rT, rA, rxa, rn, _ = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t, lo, hi, report_all=True)
+    assert np.count_nonzero(rT < 0) > 20 and rA[3] == -1
+    for ff in (0, 1):
+        with Scanner(device=0, farfield=ff) as sc:
+            sc.set_option('report_all', 1)
+            sc.load(prob)
+            T, iA, ix, ia, ns = sc.scan(t, lo, hi)
+            sc.set_option('report_all', 0)
+            T0, iA0, *_ = sc.scan(t, lo, hi)
+        xa = np.where(iA >= 0, ix * prob.n_a + ia, -1)
+        assert np.array_equal(iA, rA) and np.array_equal(xa, rxa) and np.array_equal(ns, rn)
+        assert np.all(np.abs(T - rT) <= 1e-9 * np.maximum(np.abs(rT), 1.))
+        assert np.all(T0 >= 0) and np.all((iA0 >= 0) == (rT > 0))          # the reference's rule again
+
+
+def test_thousands_of_classes():
+    """Inputs with many sample sizes have thousands of (k, n) classes (the reference supports them,
+    v1:331-355): 2 400 classes here, most of them with no site in any one window.  Parity with the oracle in
+    all kernel modes, and the time per (centre, A) item for the record."""
+    from ballermixplus_b200.native import Scanner, ScanProblem
+    rng = np.random.default_rng(23)
+    n_sites, C, n_x, n_a = 60000, 2400, 5, 21
+    g = np.sort(rng.random(n_sites)) * 0.05
+    w = rng.random(C) ** 4 + 1e-4
+    w[:3] += 2.0                                               # three big classes, a long tail of rare ones
+    cls = rng.choice(C, size=n_sites, p=w / w.sum()).astype(np.int32)
+    G = rng.random(C) * 0.1 + 1e-3
+    SP = G[None, :] * 10.0 ** rng.normal(0, 0.4, (n_x * n_a, C))
+    A = np.array([300., 1000., 3000., 1e4, 1e5])
+    prob = ScanProblem(g, cls, G, SP, A, n_x, n_a)
+    c = rng.integers(0, n_sites, 48)
+    t, lo, hi = g[c], np.zeros(48, np.int64), np.full(48, n_sites - 1, np.int64)
+    for group, ff in ((1, 0), (4, 0), (4, 1)):
+        T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, group=group, farfield=ff)
+        assert not bad
+    call = np.arange(0, n_sites, 30)
+    with Scanner(device=0).load(prob) as sc:
+        sc.set_option('timing', 1)
+        sc.scan(g[call], np.zeros(len(call), np.int64), np.full(len(call), n_sites - 1, np.int64))
+        ms, _ = sc.kernel_ms()
+        cnt = sc.counters_all()
+    print(f'{C} classes: {len(call) * len(A)} items in {ms:.1f} ms = {1e3 * ms / (len(call) * len(A)):.1f} us/item, '
+          f'{cnt["pairs"] / (len(call) * len(A)):.0f} sites per item')
+
+
+def test_cli_under_torchrun_nccl(tmp_path):
+    """`torchrun --nproc-per-node 2 -m ballermixplus_b200 ...` with one GPU per rank: rows go from the scan
+    kernel to the NCCL gather without leaving the device; rank 0 writes the same file.  Needs two GPUs."""
+    import subprocess
+    import sys
+    from ballermixplus_b200 import native
+    if native.device_count() < 2:
+        pytest.skip('needs at least two GPUs')
+    argv, gold = CASES['Example2_B2']
+    out = str(tmp_path / 'out.txt')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', '29541', '-m', 'ballermixplus_b200'] + util.abs_paths(argv) + ['-o', out]
+    res = subprocess.run(cmd, cwd=util.ROOT, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    with open(out) as fh:
+        lines = fh.read().splitlines(keepends=True)
+    n, same, worst, ties = util.compare_scan(lines, gold)
+    assert n == len(lines)
+
+
+def _cli_vs_oracle(argv, tmp_path, prove_ties=False):
     """Run the CLI on the GPU and the same host pipeline with the C oracle as the kernel."""
     from oracle import oracle_c
     from ballermixplus_b200 import windows
@@ -234,7 +313,11 @@ def _cli_vs_oracle(argv, tmp_path, near_ties=0):
     with open(ref_path, 'w') as fh:
         fh.write(HEADER)
         fh.writelines(format_rows(plan, order, T, iA, ix, ia, ns))
-    return lines, util.compare_scan(lines, ref_path, rtol=1e-9, max_near_ties=near_ties)
+    tie_rows = [] if prove_ties else None
+    res = util.compare_scan(lines, ref_path, rtol=1e-9, tie_rows=tie_rows)
+    if tie_rows:
+        util.assert_ties(argv, tie_rows)
+    return lines, res
 
 
 D = 'data/'
@@ -248,11 +331,11 @@ def test_flags_the_reference_crashes_on(tmp_path):
     b, _ = _cli_vs_oracle(ex1 + ['--listA', '500,1500,2500,3500,4500', '-s', '40'], tmp_path)
     assert a == b and len(a) == 20
     # the --findPos x grid holds both x and 1-x, whose folded tables are mathematically identical:
-    # every row is an exact tie between the two, resolved by rounding (hence near_ties = all rows)
-    lines, (n, same, worst, ties) = _cli_vs_oracle(ex1 + ['--findPos', '-s', '60'], tmp_path, near_ties=14)
+    # every row is an exact tie between the two, resolved by rounding: each differing row is proved a tie
+    lines, (n, same, worst, ties) = _cli_vs_oracle(ex1 + ['--findPos', '-s', '60'], tmp_path, prove_ties=True)
     assert n == 14 and all(float(l.split('\t')[3]) < 1.0 for l in lines[1:])
     b1 = ['-i', D + 'Example2_balancing_10MYA_DAF.txt', '--spect', D + 'HC_CEU_Neut_config_for_B1.txt', '--noFreq']
-    _cli_vs_oracle(b1 + ['--minCount', '2', '-s', '70', '--listA', '100,1000,1e4'], tmp_path, near_ties=1)
+    _cli_vs_oracle(b1 + ['--minCount', '2', '-s', '70', '--listA', '100,1000,1e4'], tmp_path, prove_ties=True)
 
 
 def test_calcballer_drop_in_one_centre_at_a_time():
