@@ -6,9 +6,9 @@ Mirrors ``NormalizedBetaBinom`` of the reference
 returning the per-site normalised probabilities.  The table is built per
 (k, n) CLASS, not per site: ``classProbs[(x, a)]`` is float64[C].  The arithmetic
 is the reference's, call for call, so the entries are bit-identical to the
-reference's per-site values (tests/test_host_tables.py checks that against the
-reference itself when /root/reference is present, and against committed
-fixtures otherwise):
+reference's per-site values (tests/test_reference_objects.py checks that against the
+reference itself when /root/reference is present; tests/test_host_pipeline.py checks the
+per-class tables against the oracle's per-site restatement everywhere):
 
   b(x, a) = a/x - a                                                   (v1:316)
   BB_x(j) = scipy.stats.betabinom(n, a, b(x, a)).pmf(j)                (v1:366-371)

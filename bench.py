@@ -496,13 +496,14 @@ def cuda_arm(opt, rank, world, local_rank):
     side = [torch.cuda.Stream(device=dev) for _ in range(max(1, opt.streams))]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def scan_into(sh, reload_problem=False):
+    def scan_into(sh, reload_problem=False, n_streams=None):
         """One step on this rank: every chromosome of the shard, then pack + gather (the only collective)."""
         fork = torch.cuda.Event()
         fork.record(main_stream)
         o = 0
+        use = side[:n_streams] if n_streams else side
         for k, (c, _) in enumerate(sh.mine):
-            st = side[k % len(side)]
+            st = use[k % len(use)]
             st.wait_event(fork)
             with torch.cuda.stream(st):
                 if reload_problem:
@@ -576,8 +577,12 @@ def cuda_arm(opt, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ms, gathered = timed(lambda: scan_into(shard), opt.steps)
-    cnt, kernel_ms, kernel_launches = collect(shard)
     clocks = sampler.stop() if rank == 0 else None
+    # roofline pass: the same step once more on ONE stream, so that the CUDA events the library records around
+    # every scan_kernel launch time that kernel alone (on several streams the launches overlap at their tails
+    # and the per-launch durations would count the shared time twice)
+    timed(lambda: scan_into(shard, n_streams=1), 1)
+    cnt, kernel_ms, kernel_launches = collect(shard)
     pairs_all, launches_all = (int(v) for v in reduce_sum([cnt['pairs'], cnt['launches']]))
     value = total_centres * n_grid * opt.steps / (ms * 1e-3)
     resident_rows = sharding.unpack_rows(gathered.cpu(), torch) if rank == 0 else None
@@ -709,9 +714,9 @@ def cuda_arm(opt, rank, world, local_rank):
             'frac_of_nominal': (achieved / FP64_NOMINAL_TFLOPS) if achieved else None,
             'kernel_ms_per_launch': kernel_ms / max(1, kernel_launches), 'launches_timed': kernel_launches,
             'kernel_share_of_step': kernel_ms / (ms / opt.steps) if ms > 0 else None,
-            'timing': 'CUDA events recorded by the library around every scan_kernel launch of the last timed step, '
-                      f'on the launching stream; {len(side)} streams, so launches overlap at their tails and the '
-                      'summed durations slightly exceed the step',
+            'timing': 'CUDA events recorded by the library around every scan_kernel launch, on the launching stream, '
+                      f'in one extra step run on a single stream right after the timed region (the timed steps rotate '
+                      f'the launches over {len(side)} streams, where per-launch events would overlap)',
             'algorithmic_flops_per_launch': flops / max(1, kernel_launches),
             'work': {k: cnt[k] for k in ('pairs', 'single', 'quads', 'far_sites', 'far_blocks', 'edge_sites', 'far_terms')},
             'sites_far_frac': cnt['far_sites'] / max(1, cnt['pairs']),

@@ -53,13 +53,19 @@ def main():
     os.makedirs(dst, exist_ok=True)
     out = [f'# ncu summary `{tag}`', '',
            'Produced by `tools/profile.sh` on a B200 (gpurun) and `tools/summarise_profile.py` here.',
-           'Command profiled: `python bench.py --sites 1000000 --steps 1 --warmup 3 --no-cpu ' + ' '.join(sys.argv[2:]) + '`',
+           'Command profiled: `python bench.py --sites 10000000 --steps 1 --warmup 3 --profile ' + ' '.join(sys.argv[2:]) + '`'
+           ' -- the benchmark\'s own configuration (10 M sites / 22 chromosomes, -s 1024); the captured launches are',
+           'chromosome 1 (846 k sites, 827 centres x 100 A) and chromosome 2.',
            '(ncu launch times are cold-cache and serialised: compare shares, not absolutes).', '']
 
     # ---- launch list
     lpath = os.path.join(src, f'{tag}_launches.csv')
-    shutil.copyfile(lpath, os.path.join(dst, f'{tag}_launches.csv'))
-    rows = [r for r in csv.reader(open(lpath)) if len(r) > 5]
+    if not os.path.exists(lpath):
+        lpath = None
+        out += ['(no launch list in this capture)', '']
+    else:
+        shutil.copyfile(lpath, os.path.join(dst, f'{tag}_launches.csv'))
+    rows = [r for r in csv.reader(open(lpath)) if len(r) > 5] if lpath else [['Kernel Name', 'Metric Value']]
     hdr = rows[0]
     ik, iv = hdr.index('Kernel Name'), hdr.index('Metric Value')
     agg = collections.OrderedDict()
@@ -71,9 +77,9 @@ def main():
         a = agg.setdefault(r[ik], [0, 0.0])
         a[0] += 1
         a[1] += v
-    tot = sum(a[1] for a in agg.values())
-    own = sum(a[1] for k, a in agg.items() if 'dfma_peak' not in k)
-    with open(os.path.join(dst, f'{tag}_launches_by_kernel.csv'), 'w') as fh:
+    tot = sum(a[1] for a in agg.values()) or 1.0
+    own = sum(a[1] for k, a in agg.items() if 'dfma_peak' not in k) or 1.0
+    with open(os.path.join(dst, f'{tag}_launches_by_kernel.csv') if lpath else os.devnull, 'w') as fh:
         fh.write('kernel,launches,total_ns,share_of_all,share_without_peak_probe\n')
         out += ['## Launch list (gpu__time_duration.sum)', '',
                 '| kernel | launches | total ms | share | share w/o the FP64-peak probe |', '|---|---|---|---|---|']
@@ -106,7 +112,18 @@ def main():
     dmul = get('smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed')
     dadd = get('smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed')
     peak = get('sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained')
-    out += ['## scan_kernel<16,4>, first captured launch (`ncu --set full`)', '',
+    # algorithmic HBM bytes of the captured launch (chromosome 1): site arrays 20 B/site, the R table, the far-field
+    # block + superblock moments of the chromosome, candidates written and re-read
+    algo = None
+    try:
+        sys.path.insert(0, ROOT)
+        import bench
+        n1 = bench.genome_sizes(10_000_000)[0]
+        items = len(range(0, n1, bench.BASE_STRIDE)) * 100
+        algo = 20.0 * n1 + 8.0 * 512 * 200 + (n1 // 32 + n1 // 256) * 100 * 2 * 256.0 + 2 * 16.0 * items
+    except Exception:
+        pass
+    out += ['## scan_kernel<16,4,far>, first captured launch (`ncu --set full`)', '',
             f'* duration {r[hdr.index("gpu__time_duration.sum")]} {units[hdr.index("gpu__time_duration.sum")]}, '
             f'grid {r[hdr.index("launch__grid_size")]} x {r[hdr.index("launch__block_size")]} threads, '
             f'{r[hdr.index("launch__registers_per_thread")]} registers/thread, '
@@ -120,16 +137,19 @@ def main():
             f'{get("smsp__warps_eligible.avg.per_cycle_active"):.2f} eligible per scheduler cycle; '
             f'issue slots used {100 * get("smsp__issue_active.avg.per_cycle_active"):.0f}%',
             f'* DRAM traffic: {dram / 1e6:.2f} MB per launch '
-            f'({get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"):.3f}% of DRAM peak): the site arrays and '
-            f'the 0.8 MB table are L2/L1 resident, the kernel is FP64-bound',
+            f'({get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"):.3f}% of DRAM peak)'
+            + (f'; algorithmic HBM bytes of this launch (site arrays + table + block moments + candidates) '
+               f'{algo / 1e6:.0f} MB -> traffic / algorithmic = {dram / algo:.2f}' if algo else '')
+            + ': the kernel is FP64-bound',
             '* top stall reasons (warps per issue): '
             + ', '.join(f'{k.split("stalled_")[1].split("_per_")[0]} {get(k):.2f}' for k in KEYS if 'issue_stalled' in k),
             '', f'All selected metrics for every captured launch: `{tag}_scan_kernel_metrics.csv`.', '']
     with open(os.path.join(dst, f'{tag}_summary.md'), 'w') as fh:
         fh.write('\n'.join(out))
     with open(os.path.join(dst, 'traffic.json'), 'w') as fh:
-        json.dump({'dram_bytes_per_launch': dram, 'source': f'{tag}_prof.ncu-rep, scan_kernel<16,4>, '
-                   'dram__bytes_read.sum + dram__bytes_write.sum, bench.py --sites 1000000'}, fh)
+        json.dump({'dram_bytes_per_launch': dram, 'algorithmic_bytes_of_that_launch': algo,
+                   'source': f'{tag}_prof.ncu-rep, scan_kernel<16,4,far>, launch of chromosome 1 (846 k sites), '
+                   'dram__bytes_read.sum + dram__bytes_write.sum, bench.py --sites 10000000 --profile'}, fh)
     print('\n'.join(out))
 
 
