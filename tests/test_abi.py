@@ -26,6 +26,24 @@ def test_library_exports_every_declared_symbol():
     assert L.blmx_abi_version() == 2
 
 
+def test_mgpu_library_exports_its_header():
+    """libblmx_mgpu.so (built where nccl.h exists) = every symbol of blmx.h plus the two of blmx_mgpu.h."""
+    import ctypes
+    path = os.path.join(util.ROOT, 'ballermixplus_b200', 'libblmx_mgpu.so')
+    if not os.path.exists(path):
+        pytest.skip('libblmx_mgpu.so not built (no nccl.h)')
+    with open(os.path.join(util.ROOT, 'include', 'blmx_mgpu.h')) as fh:
+        text = re.sub(r'/\*.*?\*/', '', fh.read(), flags=re.S)
+    extra = sorted(set(re.findall(r'\b(blmx_[a-z0-9_]+)\s*\(', text)))
+    assert extra == ['blmx_scan_sharded', 'blmx_shard_ranges']
+    try:
+        L = ctypes.CDLL(path)
+    except OSError as exc:
+        pytest.skip(f'cannot load libblmx_mgpu.so here: {exc}')
+    for n in extra + _declared():
+        assert hasattr(L, n), n
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(util.ROOT, 'ballermixplus_b200')
     for dirpath, _, files in os.walk(pkg):

@@ -461,6 +461,21 @@ def test_cli_under_torchrun_two_ranks(tmp_path):
     assert n == len(lines)
 
 
+def test_c_abi_multi_gpu_entry():
+    """blmx_scan_sharded (include/blmx_mgpu.h): one thread per GPU, NCCL communicator from ncclCommInitAll, rows
+    on rank 0 identical to a single-GPU scan.  Runs tools/mgpu_abi_demo.py in a process without torch."""
+    import subprocess
+    import sys
+    from ballermixplus_b200 import native
+    if native.device_count() < 2:
+        pytest.skip('needs at least two GPUs')
+    if not os.path.exists(os.path.join(util.ROOT, 'ballermixplus_b200', 'libblmx_mgpu.so')):
+        pytest.skip('libblmx_mgpu.so not built')
+    res = subprocess.run([sys.executable, os.path.join(util.ROOT, 'tools', 'mgpu_abi_demo.py'), '--gpus', '2'],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and 'OK:' in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
+
+
 def test_oneshot_and_timing_entry_points():
     """blmx_scan_oneshot (create + load + scan + destroy) and the per-launch kernel timing."""
     import ctypes as C
