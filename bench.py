@@ -592,8 +592,8 @@ def cuda_arm(opt, rank, world, local_rank):
     if opt.farfield and world == 1 and not opt.profile:
         for c, _ in mine:
             scanners[c].set_option('farfield', 0)
-        scan_into(shard)
-        d_ms, _ = timed(lambda: scan_into(shard), 1, flush_l2=False)
+        scan_into(shard, n_streams=1)
+        d_ms, _ = timed(lambda: scan_into(shard, n_streams=1), 1, flush_l2=False)     # one stream: exact per-launch events
         d_cnt, d_kms, d_kn = collect(shard)
         direct = (d_ms, d_cnt, d_kms, d_kn)
         for c, _ in mine:
