@@ -722,6 +722,7 @@ def cuda_arm(opt, rank, world, local_rank):
             'sites_far_frac': cnt['far_sites'] / max(1, cnt['pairs']),
             'traffic': traffic.get('dram_bytes_per_launch') if traffic else None,
             'traffic_source': traffic.get('source') if traffic else None,
+            'traffic_algorithmic_bytes_same_launch': traffic.get('algorithmic_bytes_of_that_launch') if traffic else None,
             'hbm': {'algorithmic_bytes_per_launch': hbm_algo,
                     'achieved_gbs': hbm_algo / (k_s / max(1, kernel_launches)) / 1e9 if k_s > 0 else None,
                     'peak_gbs': hbm_peak, 'moment_bytes_resident': moment_bytes,
