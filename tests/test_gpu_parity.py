@@ -399,8 +399,9 @@ print('VIOLATIONS', bad)
 
 def test_full_size_chromosome_properties():
     """BASELINE.json's full size (chromosome 1 of the 10 M-site genome: 846 k sites, n = 200,
-    100 A x 510 grid, windows of up to 53 k sites): the two kernel modes agree on 96 centres, the
-    C oracle confirms two of them, and centres give the same row whatever batch they travel in."""
+    100 A x 510 grid, windows of up to 53 k sites): the two kernel modes agree on 160 centres, the
+    C oracle confirms >= 16 centres whose row carries a real maximum (T > 0) plus 8 more with option
+    report_all (a real T on every one of them), and centres give the same row whatever batch they travel in."""
     import bench
     from oracle import oracle_c
     from ballermixplus_b200.native import Scanner
@@ -409,7 +410,7 @@ def test_full_size_chromosome_properties():
     prob = bench.make_problem([chrom])[0]
     n = len(prob.genpos)
     assert n > 800_000
-    c = np.linspace(0, n - 1, 96).astype(np.int64)
+    c = np.linspace(0, n - 1, 160).astype(np.int64)
     t, lo, hi = prob.genpos[c], np.zeros(len(c), np.int64), np.full(len(c), n - 1, np.int64)
     with Scanner(device=0, farfield=1).load(prob) as sc:
         far = sc.scan(t, lo, hi)
@@ -424,13 +425,28 @@ def test_full_size_chromosome_properties():
     assert np.all(np.abs(far[0] - direct[0]) <= 1e-10 * np.maximum(np.abs(direct[0]), 1.))
     for a, b in zip(far[1:], direct[1:]):
         assert np.array_equal(a, b)
-    assert cnt['pairs'] > 96 * 100 * 10_000              # ~12.7 k sites per (centre, A) on average
-    pick = np.array([1, 48])
+    assert cnt['pairs'] > 160 * 100 * 10_000             # ~12.7 k sites per (centre, A) on average
+    # the oracle on centres whose row carries a real maximum (neutral data: about a quarter of them) ...
+    winners = np.flatnonzero(far[1] >= 0)
+    assert len(winners) >= 16, len(winners)
+    pick = winners[np.linspace(0, len(winners) - 1, 20).astype(np.int64)]
     rT, rA, rxa, rn, _ = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t[pick], lo[pick], hi[pick])
     got_xa = np.where(far[1][pick] >= 0, far[2][pick] * prob.n_a + far[3][pick], -1)
+    assert np.count_nonzero(rA >= 0) >= 16
     assert np.array_equal(far[1][pick], rA) and np.array_equal(got_xa, rxa)
     assert np.array_equal(far[4][pick], rn)
     assert np.all(np.abs(far[0][pick] - rT) <= 1e-9 * np.maximum(np.abs(rT), 1.))
+    # ... and, with report_all on both sides, on centres whose ordinary row is all-zero
+    losers = np.flatnonzero(far[1] < 0)[:8]
+    rT, rA, rxa, rn, _ = oracle_c.scan(prob.genpos, prob.cls, prob.G, prob.SP, prob.A, t[losers], lo[losers],
+                                       hi[losers], report_all=True)
+    with Scanner(device=0, farfield=1) as sc:
+        sc.set_option('report_all', 1)
+        sc.load(prob)
+        aT, aA, ax, aa, an = sc.scan(t[losers], lo[losers], hi[losers])
+    assert np.all(rA >= 0) and np.all(rT <= 0)
+    assert np.array_equal(aA, rA) and np.array_equal(ax * prob.n_a + aa, rxa) and np.array_equal(an, rn)
+    assert np.all(np.abs(aT - rT) <= 1e-9 * np.maximum(np.abs(rT), 1.))
 
 
 def test_randomised_parity_campaign():
