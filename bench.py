@@ -48,7 +48,8 @@ FLOP_GROUPED = 2.25        # four sites: 4 FMA (quartic in R) + 1 MUL
 FLOP_EXP = 34.0            # alpha = exp(-A*|g - t|): once per (centre, A, site) evaluated site by site
 FLOP_QUAD_COEF = 23.0 / 4  # f0..f4 of a quartic from its four alphas (one lane), per grouped site
 FLOP_LOG = 47.0 + 3.0      # one log + exponent fold-in per (centre, A, grid point)
-FLOP_BLOCK = 32 * (FLOP_EXP + 2.0)   # far field: one exp + one FMA on each of the 32 moment lanes, per block visit
+FLOP_BLOCK = FLOP_EXP + 32 * (10.0 + 2.0)   # far field, per unit visit: one exp, then on each of the 32 moment lanes
+                                            # ten multiplications (power by squaring) and one FMA
 FLOP_EDGE = 9.0            # far field: five moments of a block-remainder site (besides its exp)
 FLOP_POLY = 2.0            # far field: one Horner FMA per polynomial term and grid point
 
