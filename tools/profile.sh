@@ -21,4 +21,4 @@ $cmd > gpurun_out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 66 -c 2 \
     -o gpurun_out/${tag}_prof $cmd > gpurun_out/${tag}_ncu_full.log 2>&1
 fi
-tail -1 gpurun_out/${tag}_plain*.log | cut -c1-300
+for f in gpurun_out/${tag}_plain*.log; do tail -n 1 "$f" | cut -c1-300; done
