@@ -481,6 +481,13 @@ def cuda_arm(opt, rank, world, local_rank):
     chroms = make_genome(opt.sites)
     problems = make_problem(chroms)
     del chroms
+    # the host copies of the inputs live in pinned memory: blmx_load's H2D copies are then true async DMA
+    pinned_inputs = []
+    for p in problems:
+        for name in ('genpos', 'cls'):
+            buf = torch.from_numpy(getattr(p, name)).pin_memory()
+            pinned_inputs.append(buf)
+            setattr(p, name, buf.numpy())
     stride = max(1, BASE_STRIDE // world)
     n_xa = problems[0].n_x * problems[0].n_a
     n_A = len(problems[0].A)
