@@ -780,7 +780,7 @@ def main():
     ap.add_argument('--group', type=int, default=4, choices=[1, 4])
     ap.add_argument('--farfield', type=int, default=1, choices=[0, 1],
                     help='1 (default): far sites enter through power sums; 0: every site evaluated directly')
-    ap.add_argument('--streams', type=int, default=2, help='CUDA streams the per-chromosome launches rotate over')
+    ap.add_argument('--streams', type=int, default=3, help='CUDA streams the per-chromosome launches rotate over')
     ap.add_argument('--strong-stride', type=int, default=128,
                     help='centre stride of the fixed-work (strong scaling) leg; 0 = skip it')
     ap.add_argument('--strong-steps', type=int, default=1)
