@@ -215,6 +215,29 @@ def test_synthetic_n200_against_oracle_sample():
         assert np.array_equal(a, b)
 
 
+def test_default_grid_with_windows_of_100k_sites():
+    """The reference's default A grid starts at A = 100 (v1:162): on a 150 k-site chromosome such a window holds
+    ~130 k sites and the far field runs over hundreds of superblocks; at the other end A = 1e8 leaves a window of a
+    few sites.  24 centres (ends included), all kernel modes' far/direct agreement, the oracle on every one."""
+    import bench
+    from ballermixplus_b200.native import Scanner
+    chrom = bench.make_chromosome(150000, seed=77)
+    prob = bench.make_problem([chrom], range_a=None)[0]
+    assert len(prob.A) == 31 and prob.A.min() == 100.0
+    n = len(prob.genpos)
+    c = np.concatenate(([0, 1, n - 2, n - 1], np.linspace(5, n - 6, 20).astype(np.int64)))
+    t, lo, hi = prob.genpos[c], np.zeros(len(c), np.int64), np.full(len(c), n - 1, np.int64)
+    mid = prob.genpos[n // 2]
+    assert np.count_nonzero(np.exp(-100.0 * np.abs(prob.genpos - mid)) >= 1e-8) > 100_000     # the A = 100 window
+    T, iA, ix, ia, ns, bad = _check_against_oracle(prob, t, lo, hi, farfield=1)      # CLR, site pairs: asserted inside
+    assert not bad, (bad, iA[bad], ns[bad])
+    with Scanner(device=0, farfield=0).load(prob) as sc:
+        direct = sc.scan(t, lo, hi)
+    assert np.all(np.abs(T - direct[0]) <= 1e-10 * np.maximum(np.abs(direct[0]), 1.))
+    for a, b in zip((iA, ix, ia, ns), direct[1:]):
+        assert np.array_equal(a, b)
+
+
 def test_report_all_reports_the_best_grid_point_whatever_its_sign():
     """Option report_all (the maximum starts from -inf instead of the reference's 0, v1:451): on neutral
     synthetic data most centres have no grid point with T > 0, so the ordinary rows are all-zero and compare
