@@ -26,7 +26,7 @@ def random_problem(rng, big=False):
         C = int(rng.choice([1, 2, 5, 12]))
     else:
         n_sites = int(rng.choice([1, 2, 5, 40, 300, 2000, 20000]))
-        C = int(rng.choice([1, 2, 3, 17, 60, 250]))
+        C = int(rng.choice([1, 2, 3, 17, 60, 250, 1200]))
     n_x = int(rng.choice([1, 2, 5, 10]))
     n_a = int(rng.choice([1, 3, 7, 51, 70]))
     n_A = int(rng.choice([1, 2, 9, 40]))
