@@ -396,7 +396,7 @@ def reference_arm(opt, rank):
     # a bounded sample per step: about 12 s of CPU work, less when many steps are asked for, so that the whole
     # arm (steps + one run of the unmodified script) ends within a few minutes
     per_step = opt.cpu_centres or cpu_sample_size(problems, plans, threads,
-                                                  target_s=max(3.0, min(12.0, 150.0 / max(1, opt.steps))))
+                                                  target_s=max(3.0, min(12.0, 100.0 / max(1, opt.steps))))
     sample = cpu_sample(problems, plans, per_step, threads)
     for _ in range(min(opt.warmup, 2)):
         run_cpu_oracle(problems, plans, cpu_sample(problems, plans, 1, threads), threads)
